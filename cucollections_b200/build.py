@@ -1,0 +1,123 @@
+"""Builds the C-ABI shared libraries with nvcc for sm_100a (no GPU needed to build).
+
+  libcuco_b200.so            cucollections_b200/csrc/cabi_*.cu  against  include/            (the product)
+  oracle/_ref/libcuco_ref.so the same shim                      against  /root/reference/include
+                             (cuco's own build: parity oracle + "cuco on the same B200" bench arm;
+                              only built when the reference tree is present, i.e. in the dev
+                              container - the GPU box uses the prebuilt file)
+
+Objects are cached under cucollections_b200/_build and oracle/_build keyed by a hash of the command
+line and of every header/source that can influence them, so repeated calls are cheap.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "cucollections_b200" / "csrc"
+NATIVE_LIB = ROOT / "cucollections_b200" / "libcuco_b200.so"
+REF_LIB = ROOT / "oracle" / "_ref" / "libcuco_ref.so"
+REFERENCE_INCLUDE = Path("/root/reference/include")
+NUM_KINDS = 10
+# kinds whose launch parameters can be switched at run time (bench / sweep configurations)
+TUNABLE_KINDS = {0, 1, 2, 3}
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+COMMON = [
+    "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "--expt-extended-lambda",
+    "--expt-relaxed-constexpr",
+    "-O3",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=hidden",
+    "-diag-suppress", "20012,20011,177",
+]
+
+
+def _tree_hash(paths) -> str:
+    h = hashlib.sha256()
+    for root in paths:
+        root = Path(root)
+        files = [root] if root.is_file() else sorted(p for p in root.rglob("*") if p.is_file())
+        for f in files:
+            h.update(str(f).encode())
+            h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def _compile(job):
+    src, obj, flags, stamp = job
+    stamp_file = obj.with_suffix(".stamp")
+    if obj.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return obj, 0.0, ""
+    cmd = [NVCC, *COMMON, *flags, "-c", str(src), "-o", str(obj)]
+    import time
+    t0 = time.time()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    stamp_file.write_text(stamp)
+    return obj, time.time() - t0, res.stderr
+
+
+def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], reference: bool, verbose: bool):
+    build_dir.mkdir(parents=True, exist_ok=True)
+    lib.parent.mkdir(parents=True, exist_ok=True)
+    dep_hash = _tree_hash([CSRC, include / "cuco", ROOT / "include" / "cuco_b200.h"])
+    jobs = []
+    base = [f"-I{include}", *extra]
+    jobs.append((CSRC / "cabi_core.cu", build_dir / "cabi_core.o", base, ""))
+    for k in range(NUM_KINDS):
+        flags = [*base, f"-DCUCO_SHIM_KIND={k}"]
+        if not reference and k in TUNABLE_KINDS:
+            flags.append("-DCUCO_B200_TUNABLE=1")
+        jobs.append((CSRC / "cabi_kind.cu", build_dir / f"cabi_kind_{k}.o", flags, ""))
+    jobs = [(s, o, f, hashlib.sha256((dep_hash + " ".join(map(str, f)) + " ".join(COMMON)).encode()).hexdigest())
+            for (s, o, f, _) in jobs]
+    workers = max(1, min(len(jobs), (os.cpu_count() or 4)))
+    objs = []
+    with cf.ThreadPoolExecutor(workers) as pool:
+        for obj, secs, err in pool.map(_compile, jobs):
+            objs.append(obj)
+            if verbose and secs:
+                print(f"  built {obj.name} in {secs:.1f}s", file=sys.stderr)
+            if verbose and err.strip():
+                print(err, file=sys.stderr)
+    newest = max(o.stat().st_mtime for o in objs)
+    if not lib.exists() or lib.stat().st_mtime < newest:
+        cmd = [NVCC, "-shared", "-o", str(lib), *map(str, objs), "-lcudart"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed: {' '.join(cmd)}\n{res.stderr}")
+        if verbose:
+            print(f"  linked {lib}", file=sys.stderr)
+    return lib
+
+
+def build_native(verbose: bool = False) -> Path:
+    """Compiles the product library (hand-written sm_100a kernels behind the cuco:: surface)."""
+    return _build_lib(NATIVE_LIB, ROOT / "cucollections_b200" / "_build", ROOT / "include", [], False, verbose)
+
+
+def build_reference(verbose: bool = False) -> Path | None:
+    """Compiles cuco's own headers behind the same shim into oracle/_ref (dev container only)."""
+    if not REFERENCE_INCLUDE.is_dir():
+        return REF_LIB if REF_LIB.exists() else None
+    return _build_lib(REF_LIB, ROOT / "oracle" / "_build", REFERENCE_INCLUDE,
+                      ["-DCUCO_SHIM_REFERENCE=1"], True, verbose)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["native", "reference"]
+    if "native" in which:
+        print(build_native(verbose=True))
+    if "reference" in which:
+        print(build_reference(verbose=True))

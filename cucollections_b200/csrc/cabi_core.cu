@@ -1,0 +1,551 @@
+// extern "C" entry points of include/cuco_b200.h: argument checking, exception -> status code
+// translation, dispatch to the per-kind tables (cabi_kind.cu), launch tuning, and the routing
+// kernels of the hash-partitioned multi-GPU table. Compiled into both libcuco_b200.so (native) and
+// oracle/_ref/libcuco_ref.so (reference build of the same shim; -DCUCO_SHIM_REFERENCE).
+#include "cabi_table.hpp"
+
+#include "../../include/cuco_b200.h"
+
+#if !defined(CUCO_SHIM_REFERENCE)
+#include <cuco/b200/bulk_engine.cuh>
+#endif
+
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+#include <cstring>
+#include <exception>
+#include <new>
+#include <stdexcept>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f) noexcept
+{
+  try {
+    f();
+    g_last_error.clear();
+    return 0;
+  } catch (std::bad_alloc const& e) {
+    g_last_error = std::string{"out of memory: "} + e.what();
+    return 2;
+  } catch (std::logic_error const& e) {  // cuco::logic_error, std::invalid_argument
+    g_last_error = e.what();
+    return 3;
+  } catch (std::exception const& e) {  // cuco::cuda_error and anything else
+    g_last_error = e.what();
+    return 4;
+  } catch (...) {
+    g_last_error = "unknown exception";
+    return 5;
+  }
+}
+
+void require(bool ok, char const* what)
+{
+  if (!ok) { throw std::invalid_argument(what); }
+}
+
+cuco_shim_factory const g_factories[CUCO_B200_NUM_KINDS] = {
+  cuco_shim_make_kind_0, cuco_shim_make_kind_1, cuco_shim_make_kind_2, cuco_shim_make_kind_3,
+  cuco_shim_make_kind_4, cuco_shim_make_kind_5, cuco_shim_make_kind_6, cuco_shim_make_kind_7,
+  cuco_shim_make_kind_8, cuco_shim_make_kind_9};
+
+void check_launch()
+{
+  auto const status = cudaPeekAtLastError();
+  if (status != cudaSuccess) {
+    cudaGetLastError();
+    throw std::runtime_error(std::string{"kernel launch failed: "} + cudaGetErrorString(status));
+  }
+}
+
+// ================================================================================================
+// routing kernels for the hash-partitioned table
+// ================================================================================================
+constexpr int route_block = 256;
+constexpr int route_items = 8;  // elements per thread per tile
+constexpr int max_parts   = 64;
+
+__host__ __device__ inline std::uint64_t mix64(std::uint64_t x)
+{
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+/// Owner rank of a key: high bits of a 64-bit mix that shares nothing with the in-table xxhash.
+__device__ inline int owner_of(std::uint64_t key, std::uint64_t salt, int num_parts)
+{
+  return static_cast<int>(__umul64hi(mix64(key ^ salt), static_cast<std::uint64_t>(num_parts)));
+}
+
+template <typename Key>
+__device__ inline std::uint64_t key_bits(Key k)
+{
+  if constexpr (sizeof(Key) == 4) {
+    return static_cast<std::uint64_t>(static_cast<std::uint32_t>(k));
+  } else {
+    return static_cast<std::uint64_t>(k);
+  }
+}
+
+template <typename Key, int Stride>
+__global__ __launch_bounds__(route_block) void partition_count_kernel(
+  Key const* keys, std::int64_t n, int num_parts, std::uint64_t salt, unsigned long long* counts)
+{
+  __shared__ unsigned int hist[max_parts];
+  for (int p = threadIdx.x; p < num_parts; p += route_block) {
+    hist[p] = 0;
+  }
+  __syncthreads();
+
+  constexpr std::int64_t tile = std::int64_t{route_block} * route_items;
+  for (std::int64_t base = std::int64_t{blockIdx.x} * tile; base < n;
+       base += std::int64_t{gridDim.x} * tile) {
+#pragma unroll
+    for (int j = 0; j < route_items; ++j) {
+      std::int64_t const i = base + std::int64_t{j} * route_block + threadIdx.x;
+      bool const live      = i < n;
+      int const owner      = live ? owner_of(key_bits(keys[i * Stride]), salt, num_parts) : -1;
+      // one shared-memory add per distinct owner per warp
+      unsigned const peers = __match_any_sync(0xffffffffu, owner);
+      if (live && (__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31)) {
+        atomicAdd(&hist[owner], __popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < num_parts; p += route_block) {
+    if (hist[p]) { atomicAdd(&counts[p], static_cast<unsigned long long>(hist[p])); }
+  }
+}
+
+/// Element = Key (+ Payload). AoS: one struct {Key, Payload}; SoA: two arrays.
+template <typename Key, typename Payload, bool HasPayload, bool AoS>
+__global__ __launch_bounds__(route_block) void partition_scatter_kernel(Key const* keys,
+                                                                        Payload const* values,
+                                                                        std::int64_t n,
+                                                                        int num_parts,
+                                                                        std::uint64_t salt,
+                                                                        unsigned long long* cursors,
+                                                                        Key* keys_out,
+                                                                        Payload* values_out,
+                                                                        std::int64_t* src_index)
+{
+  __shared__ unsigned int hist[max_parts];
+  __shared__ unsigned long long seg_base[max_parts];
+  constexpr int stride      = AoS ? 2 : 1;
+  constexpr std::int64_t tile = std::int64_t{route_block} * route_items;
+
+  for (std::int64_t base = std::int64_t{blockIdx.x} * tile; base < n;
+       base += std::int64_t{gridDim.x} * tile) {
+    for (int p = threadIdx.x; p < num_parts; p += route_block) {
+      hist[p] = 0;
+    }
+    __syncthreads();
+
+    Key k[route_items];
+    Payload v[route_items];
+    int owner[route_items];
+    unsigned rank[route_items];
+#pragma unroll
+    for (int j = 0; j < route_items; ++j) {
+      std::int64_t const i = base + std::int64_t{j} * route_block + threadIdx.x;
+      bool const live      = i < n;
+      owner[j]             = -1;
+      if (live) {
+        k[j] = keys[i * stride];
+        if constexpr (HasPayload) { v[j] = AoS ? reinterpret_cast<Payload const*>(keys)[i * 2 + 1] : values[i]; }
+        owner[j] = owner_of(key_bits(k[j]), salt, num_parts);
+      }
+      unsigned const peers  = __match_any_sync(0xffffffffu, owner[j]);
+      int const leader      = __ffs(peers) - 1;
+      unsigned const before = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+      unsigned start        = 0;
+      if (live && leader == static_cast<int>(threadIdx.x & 31)) {
+        start = atomicAdd(&hist[owner[j]], __popc(peers));
+      }
+      start   = __shfl_sync(0xffffffffu, start, leader);
+      rank[j] = start + before;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < num_parts; p += route_block) {
+      seg_base[p] = hist[p] ? atomicAdd(&cursors[p], static_cast<unsigned long long>(hist[p])) : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < route_items; ++j) {
+      if (owner[j] >= 0) {
+        auto const dst = seg_base[owner[j]] + rank[j];
+        if constexpr (AoS) {
+          keys_out[dst * 2]                                  = k[j];
+          reinterpret_cast<Payload*>(keys_out)[dst * 2 + 1] = v[j];
+        } else {
+          keys_out[dst] = k[j];
+          if constexpr (HasPayload) { values_out[dst] = v[j]; }
+        }
+        if (src_index != nullptr) {
+          src_index[dst] = base + std::int64_t{j} * route_block + threadIdx.x;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ __launch_bounds__(route_block) void scatter_by_index_kernel(T const* in,
+                                                                       std::int64_t const* index,
+                                                                       T* out,
+                                                                       std::int64_t n)
+{
+  for (std::int64_t i = std::int64_t{blockIdx.x} * route_block + threadIdx.x; i < n;
+       i += std::int64_t{gridDim.x} * route_block) {
+    out[index[i]] = in[i];
+  }
+}
+
+unsigned route_grid(std::int64_t n, std::int64_t per_block)
+{
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  std::int64_t const blocks = (n + per_block - 1) / per_block;
+  std::int64_t const cap    = std::int64_t{sms} * 8;
+  return static_cast<unsigned>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cuco_b200_build_info(void)
+{
+#if defined(CUCO_SHIM_REFERENCE)
+  return "reference";
+#else
+  return "native";
+#endif
+}
+
+const char* cuco_b200_last_error(void) { return g_last_error.c_str(); }
+
+int cuco_b200_create(int kind,
+                     int64_t size,
+                     double load_factor,
+                     int64_t empty_key,
+                     int64_t empty_value,
+                     int has_erased,
+                     int64_t erased_key,
+                     void* stream,
+                     cuco_b200_table** out)
+{
+  return guarded([&] {
+    require(out != nullptr, "out must not be NULL");
+    require(kind >= 0 && kind < CUCO_B200_NUM_KINDS, "unknown table kind");
+    require(!(has_erased && load_factor != 0.0),
+            "the erased-key constructor takes a capacity, not a load factor");
+    *out = g_factories[kind](size, load_factor, empty_key, empty_value, has_erased, erased_key, stream);
+  });
+}
+
+int cuco_b200_destroy(cuco_b200_table* t)
+{
+  return guarded([&] { delete t; });
+}
+
+int cuco_b200_kind_of(const cuco_b200_table* t) { return t ? t->kind() : -1; }
+int cuco_b200_key_bytes(const cuco_b200_table* t) { return t ? t->key_bytes() : -1; }
+int cuco_b200_value_bytes(const cuco_b200_table* t) { return t ? t->value_bytes() : -1; }
+int64_t cuco_b200_capacity(const cuco_b200_table* t) { return t ? t->capacity() : -1; }
+
+int cuco_b200_size(cuco_b200_table* t, void* stream, int64_t* out)
+{
+  return guarded([&] {
+    require(t && out, "NULL argument");
+    *out = t->size(stream);
+  });
+}
+
+int cuco_b200_clear(cuco_b200_table* t, void* stream)
+{
+  return guarded([&] {
+    require(t, "NULL table");
+    t->clear(stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_insert(cuco_b200_table* t,
+                     const void* keys,
+                     const void* values,
+                     int64_t n,
+                     void* stream,
+                     int64_t* num_inserted)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0), "bad argument");
+    t->insert(keys, values, n, stream, num_inserted);
+    check_launch();
+  });
+}
+
+int cuco_b200_insert_if(cuco_b200_table* t,
+                        const void* keys,
+                        const void* values,
+                        const uint8_t* stencil,
+                        int64_t n,
+                        void* stream,
+                        int64_t* num_inserted)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((keys && stencil) || n == 0), "bad argument");
+    t->insert_if(keys, values, stencil, n, stream, num_inserted);
+    check_launch();
+  });
+}
+
+int cuco_b200_find(cuco_b200_table* t, const void* keys, void* out, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((keys && out) || n == 0), "bad argument");
+    t->find(keys, out, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_contains(cuco_b200_table* t, const void* keys, uint8_t* out, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((keys && out) || n == 0), "bad argument");
+    t->contains(keys, out, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_contains_if(cuco_b200_table* t,
+                          const void* keys,
+                          const uint8_t* stencil,
+                          uint8_t* out,
+                          int64_t n,
+                          void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((keys && out && stencil) || n == 0), "bad argument");
+    t->contains_if(keys, stencil, out, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_insert_and_find(cuco_b200_table* t,
+                              const void* keys,
+                              const void* values,
+                              void* found,
+                              uint8_t* inserted,
+                              int64_t n,
+                              void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((keys && found && inserted) || n == 0), "bad argument");
+    t->insert_and_find(keys, values, found, inserted, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_insert_or_assign(
+  cuco_b200_table* t, const void* keys, const void* values, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0), "bad argument");
+    t->insert_or_assign(keys, values, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_insert_or_apply(cuco_b200_table* t,
+                              const void* keys,
+                              const void* values,
+                              int64_t n,
+                              int reduce_op,
+                              int has_init,
+                              int64_t init,
+                              void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0), "bad argument");
+    t->insert_or_apply(keys, values, n, reduce_op, has_init, init, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_erase(cuco_b200_table* t, const void* keys, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0), "bad argument");
+    t->erase(keys, n, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_retrieve_all(
+  cuco_b200_table* t, void* keys_out, void* values_out, int64_t* n_out, void* stream)
+{
+  return guarded([&] {
+    require(t && keys_out && n_out, "NULL argument");
+    *n_out = t->retrieve_all(keys_out, values_out, stream);
+  });
+}
+
+int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream)
+{
+  return guarded([&] {
+    require(t, "NULL table");
+    t->rehash(capacity, stream);
+  });
+}
+
+int cuco_b200_set_tuning(
+  int keys_per_thread, int cas_first, int sector_chunks, int waves, int force_generic, int l2_window)
+{
+#if defined(CUCO_SHIM_REFERENCE)
+  (void)keys_per_thread, (void)cas_first, (void)sector_chunks, (void)waves, (void)force_generic,
+    (void)l2_window;
+  return 1;
+#else
+  auto& t = cuco::b200::tuning();
+  if (keys_per_thread == 1 || keys_per_thread == 2 || keys_per_thread == 4) {
+    t.keys_per_thread = keys_per_thread;
+  }
+  if (cas_first >= 0) { t.cas_first = cas_first != 0; }
+  if (sector_chunks >= 0) { t.sector_chunks = sector_chunks != 0; }
+  if (waves >= 1) { t.waves = waves; }
+  if (force_generic >= 0) { t.force_generic = force_generic != 0; }
+  if (l2_window >= 0) { t.l2_window = l2_window != 0; }
+  return 0;
+#endif
+}
+
+int cuco_b200_partition_count(const void* keys,
+                              int key_bytes,
+                              int pair_aos,
+                              int64_t n,
+                              int num_parts,
+                              uint64_t salt,
+                              int64_t* counts,
+                              void* stream)
+{
+  return guarded([&] {
+    require(n >= 0 && (keys || n == 0) && counts, "bad argument");
+    require(num_parts >= 1 && num_parts <= max_parts, "num_parts must be in [1, 64]");
+    require(key_bytes == 4 || key_bytes == 8, "key_bytes must be 4 or 8");
+    if (n == 0) { return; }
+    auto const grid = route_grid(n, std::int64_t{route_block} * route_items);
+    auto* c         = reinterpret_cast<unsigned long long*>(counts);
+    auto s          = static_cast<cudaStream_t>(stream);
+    if (key_bytes == 8) {
+      auto const* k = static_cast<std::int64_t const*>(keys);
+      if (pair_aos) {
+        partition_count_kernel<std::int64_t, 2><<<grid, route_block, 0, s>>>(k, n, num_parts, salt, c);
+      } else {
+        partition_count_kernel<std::int64_t, 1><<<grid, route_block, 0, s>>>(k, n, num_parts, salt, c);
+      }
+    } else {
+      auto const* k = static_cast<std::int32_t const*>(keys);
+      if (pair_aos) {
+        partition_count_kernel<std::int32_t, 2><<<grid, route_block, 0, s>>>(k, n, num_parts, salt, c);
+      } else {
+        partition_count_kernel<std::int32_t, 1><<<grid, route_block, 0, s>>>(k, n, num_parts, salt, c);
+      }
+    }
+    check_launch();
+  });
+}
+
+int cuco_b200_partition_scatter(const void* keys,
+                                const void* values,
+                                int key_bytes,
+                                int value_bytes,
+                                int pair_aos,
+                                int64_t n,
+                                int num_parts,
+                                uint64_t salt,
+                                int64_t* cursors,
+                                void* keys_out,
+                                void* values_out,
+                                int64_t* src_index,
+                                void* stream)
+{
+  return guarded([&] {
+    require(n >= 0 && ((keys && keys_out) || n == 0) && cursors, "bad argument");
+    require(num_parts >= 1 && num_parts <= max_parts, "num_parts must be in [1, 64]");
+    require(key_bytes == 4 || key_bytes == 8, "key_bytes must be 4 or 8");
+    bool const has_payload = pair_aos || values != nullptr;
+    require(!has_payload || pair_aos || (value_bytes == key_bytes && values_out),
+            "separate value arrays must have the key width and an output");
+    if (n == 0) { return; }
+    auto const grid = route_grid(n, std::int64_t{route_block} * route_items);
+    auto* c         = reinterpret_cast<unsigned long long*>(cursors);
+    auto s          = static_cast<cudaStream_t>(stream);
+    auto launch     = [&](auto key_tag) {
+      using K       = decltype(key_tag);
+      auto const* k = static_cast<K const*>(keys);
+      auto const* v = static_cast<K const*>(values);
+      auto* ko      = static_cast<K*>(keys_out);
+      auto* vo      = static_cast<K*>(values_out);
+      if (pair_aos) {
+        partition_scatter_kernel<K, K, true, true>
+          <<<grid, route_block, 0, s>>>(k, v, n, num_parts, salt, c, ko, vo, src_index);
+      } else if (has_payload) {
+        partition_scatter_kernel<K, K, true, false>
+          <<<grid, route_block, 0, s>>>(k, v, n, num_parts, salt, c, ko, vo, src_index);
+      } else {
+        partition_scatter_kernel<K, K, false, false>
+          <<<grid, route_block, 0, s>>>(k, v, n, num_parts, salt, c, ko, vo, src_index);
+      }
+    };
+    if (key_bytes == 8) {
+      launch(std::int64_t{});
+    } else {
+      launch(std::int32_t{});
+    }
+    check_launch();
+  });
+}
+
+int cuco_b200_scatter_by_index(
+  const void* in, const int64_t* index, void* out, int elem_bytes, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(n >= 0 && ((in && index && out) || n == 0), "bad argument");
+    if (n == 0) { return; }
+    auto const grid = route_grid(n, route_block);
+    auto s          = static_cast<cudaStream_t>(stream);
+    switch (elem_bytes) {
+      case 1:
+        scatter_by_index_kernel<std::uint8_t><<<grid, route_block, 0, s>>>(
+          static_cast<std::uint8_t const*>(in), index, static_cast<std::uint8_t*>(out), n);
+        break;
+      case 4:
+        scatter_by_index_kernel<std::uint32_t><<<grid, route_block, 0, s>>>(
+          static_cast<std::uint32_t const*>(in), index, static_cast<std::uint32_t*>(out), n);
+        break;
+      case 8:
+        scatter_by_index_kernel<std::uint64_t><<<grid, route_block, 0, s>>>(
+          static_cast<std::uint64_t const*>(in), index, static_cast<std::uint64_t*>(out), n);
+        break;
+      default: throw std::invalid_argument("elem_bytes must be 1, 4 or 8");
+    }
+    check_launch();
+  });
+}
+
+}  // extern "C"

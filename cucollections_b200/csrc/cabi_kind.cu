@@ -1,0 +1,296 @@
+// One explicit instantiation of the cuco::static_map / cuco::static_set surface behind the C ABI.
+// Compile with -DCUCO_SHIM_KIND=<k>; the include root on the command line decides whether this is
+// the b200-native table (-I include) or cuco's own build (-I /root/reference/include). Only the
+// public container API is used, so both compile from this one source.
+#include "cabi_table.hpp"
+
+#include <cuco/static_map.cuh>
+#include <cuco/static_set.cuh>
+#include <cuco/utility/reduction_functors.cuh>
+
+#include <cuda/std/tuple>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <cstdint>
+#include <stdexcept>
+
+#ifndef CUCO_SHIM_KIND
+#error "define CUCO_SHIM_KIND"
+#endif
+
+namespace {
+
+using i32 = std::int32_t;
+using i64 = std::int64_t;
+
+template <typename K>
+using eq = thrust::equal_to<K>;
+template <typename K, typename V, typename Probe, int W>
+using map_t = cuco::static_map<K,
+                               V,
+                               cuco::extent<std::size_t>,
+                               cuda::thread_scope_device,
+                               eq<K>,
+                               Probe,
+                               cuco::cuda_allocator<cuco::pair<K, V>>,
+                               cuco::storage<W>>;
+template <typename K, typename Probe, int W>
+using set_t = cuco::static_set<K,
+                               cuco::extent<std::size_t>,
+                               cuda::thread_scope_device,
+                               eq<K>,
+                               Probe,
+                               cuco::cuda_allocator<K>,
+                               cuco::storage<W>>;
+
+#if CUCO_SHIM_KIND == 0
+using container_t = set_t<i32, cuco::double_hashing<4, cuco::default_hash_function<i32>>, 1>;
+#elif CUCO_SHIM_KIND == 1
+using container_t = map_t<i64, i64, cuco::linear_probing<1, cuco::default_hash_function<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 2
+using container_t = map_t<i64, i64, cuco::double_hashing<8, cuco::default_hash_function<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 3
+using container_t = map_t<i32, i32, cuco::linear_probing<4, cuco::default_hash_function<i32>>, 1>;
+#elif CUCO_SHIM_KIND == 4
+using container_t = map_t<i64, i64, cuco::linear_probing<4, cuco::default_hash_function<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 5
+using container_t = set_t<i64, cuco::double_hashing<4, cuco::default_hash_function<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 6
+using container_t = map_t<i64, i64, cuco::linear_probing<1, cuco::default_hash_function<i64>>, 2>;
+#elif CUCO_SHIM_KIND == 7
+using container_t = map_t<i32, i32, cuco::double_hashing<2, cuco::murmurhash3_32<i32>>, 2>;
+#elif CUCO_SHIM_KIND == 8
+using container_t = map_t<i32, i64, cuco::linear_probing<1, cuco::default_hash_function<i32>>, 1>;
+#elif CUCO_SHIM_KIND == 9
+using container_t = map_t<i64, i64, cuco::double_hashing<8, cuco::xxhash_64<i64>>, 1>;
+#else
+#error "unknown CUCO_SHIM_KIND"
+#endif
+using selected_container = container_t;
+
+template <typename C, typename = void>
+struct mapped_of {
+  using type = void;
+};
+template <typename C>
+struct mapped_of<C, std::void_t<typename C::mapped_type>> {
+  using type = typename C::mapped_type;
+};
+
+/// (keys[i], values[i]) -> cuco::pair, for the separate-arrays input layout.
+template <typename K, typename V>
+struct zip_to_pair {
+  K const* keys;
+  V const* values;
+  __host__ __device__ cuco::pair<K, V> operator()(std::int64_t i) const
+  {
+    return cuco::pair<K, V>{keys[i], values[i]};
+  }
+};
+
+struct nonzero {
+  __host__ __device__ bool operator()(std::uint8_t b) const { return b != 0; }
+};
+
+template <typename container_t>
+class table_impl final : public cuco_b200_table {
+  using key_type    = typename container_t::key_type;
+  using mapped_type = typename mapped_of<container_t>::type;
+  static constexpr bool is_map = !std::is_void_v<mapped_type>;
+  using payload_t   = std::conditional_t<is_map, mapped_type, key_type>;  // what find() writes
+  using slot_type   = typename container_t::value_type;
+
+ public:
+  table_impl(i64 size, double lf, i64 ek, i64 ev, int has_erased, i64 erased, void* stream)
+    : c_{make(size, lf, ek, ev, has_erased, erased, stream)}
+  {
+  }
+
+  int kind() const override { return CUCO_SHIM_KIND; }
+  int key_bytes() const override { return sizeof(key_type); }
+  int value_bytes() const override { return is_map ? sizeof(payload_t) : 0; }
+  i64 capacity() const override { return static_cast<i64>(c_.capacity()); }
+  i64 size(void* s) override { return static_cast<i64>(c_.size(sref(s))); }
+  void clear(void* s) override { c_.clear_async(sref(s)); }
+
+  void insert(const void* keys, const void* values, i64 n, void* s, i64* num) override
+  {
+    with_input(keys, values, n, [&](auto first, auto last) {
+      if (num) {
+        *num = static_cast<i64>(c_.insert(first, last, sref(s)));
+      } else {
+        c_.insert_async(first, last, sref(s));
+      }
+    });
+  }
+
+  void insert_if(const void* keys, const void* values, const std::uint8_t* st, i64 n, void* s, i64* num) override
+  {
+    with_input(keys, values, n, [&](auto first, auto last) {
+      if (num) {
+        *num = static_cast<i64>(c_.insert_if(first, last, st, nonzero{}, sref(s)));
+      } else {
+        c_.insert_if_async(first, last, st, nonzero{}, sref(s));
+      }
+    });
+  }
+
+  void find(const void* keys, void* out, i64 n, void* s) override
+  {
+    auto const* k = static_cast<key_type const*>(keys);
+    c_.find_async(k, k + n, static_cast<payload_t*>(out), sref(s));
+  }
+
+  void contains(const void* keys, std::uint8_t* out, i64 n, void* s) override
+  {
+    auto const* k = static_cast<key_type const*>(keys);
+    c_.contains_async(k, k + n, reinterpret_cast<bool*>(out), sref(s));
+  }
+
+  void contains_if(const void* keys, const std::uint8_t* st, std::uint8_t* out, i64 n, void* s) override
+  {
+    auto const* k = static_cast<key_type const*>(keys);
+    c_.contains_if_async(k, k + n, st, nonzero{}, reinterpret_cast<bool*>(out), sref(s));
+  }
+
+  void insert_and_find(const void* keys, const void* values, void* found, std::uint8_t* inserted, i64 n, void* s) override
+  {
+#if defined(CUCO_SHIM_REFERENCE) && (CUCO_SHIM_KIND == 6)
+    // nvcc 12.9 aborts ("Broken module found") on the reference's insert_and_find for 16-byte slots
+    // with storage<2>; that one operation is left out of the reference build of this kind.
+    (void)keys, (void)values, (void)found, (void)inserted, (void)n, (void)s;
+    throw std::invalid_argument("insert_and_find: not compilable in the reference build of kind 6");
+#else
+    with_input(keys, values, n, [&](auto first, auto last) {
+      c_.insert_and_find_async(
+        first, last, static_cast<payload_t*>(found), reinterpret_cast<bool*>(inserted), sref(s));
+    });
+#endif
+  }
+
+  void insert_or_assign(const void* keys, const void* values, i64 n, void* s) override
+  {
+    if constexpr (is_map) {
+      with_input(keys, values, n, [&](auto first, auto last) {
+        c_.insert_or_assign_async(first, last, sref(s));
+      });
+    } else {
+      throw std::invalid_argument("insert_or_assign is a static_map operation");
+    }
+  }
+
+  void insert_or_apply(const void* keys, const void* values, i64 n, int op, int has_init, i64 init, void* s) override
+  {
+    if constexpr (is_map) {
+      with_input(keys, values, n, [&](auto first, auto last) {
+        auto run = [&](auto functor) {
+          if (has_init) {
+            c_.insert_or_apply_async(first, last, static_cast<payload_t>(init), functor, sref(s));
+          } else {
+            c_.insert_or_apply_async(first, last, functor, sref(s));
+          }
+        };
+        switch (op) {
+          case 0: run(cuco::reduce::plus{}); break;
+          case 1: run(cuco::reduce::min{}); break;
+          case 2: run(cuco::reduce::max{}); break;
+          default: throw std::invalid_argument("unknown reduce op");
+        }
+      });
+    } else {
+      throw std::invalid_argument("insert_or_apply is a static_map operation");
+    }
+  }
+
+  void erase(const void* keys, i64 n, void* s) override
+  {
+    auto const* k = static_cast<key_type const*>(keys);
+    c_.erase_async(k, k + n, sref(s));
+  }
+
+  i64 retrieve_all(void* keys_out, void* values_out, void* s) override
+  {
+    auto* k = static_cast<key_type*>(keys_out);
+    if constexpr (is_map) {
+      auto const ends = c_.retrieve_all(k, static_cast<payload_t*>(values_out), sref(s));
+      return static_cast<i64>(ends.first - k);
+    } else {
+      return static_cast<i64>(c_.retrieve_all(k, sref(s)) - k);
+    }
+  }
+
+  void rehash(i64 capacity, void* s) override
+  {
+    if (capacity < 0) {
+      c_.rehash(sref(s));
+    } else {
+      c_.rehash(static_cast<typename container_t::size_type>(capacity), sref(s));
+    }
+  }
+
+ private:
+  static cuda::stream_ref sref(void* s) { return cuda::stream_ref{static_cast<cudaStream_t>(s)}; }
+
+  static container_t make(i64 size, double lf, i64 ek, i64 ev, int has_erased, i64 erased, void* s)
+  {
+    auto const extent = cuco::extent<std::size_t>{static_cast<std::size_t>(size < 0 ? 0 : size)};
+    auto const ekey   = cuco::empty_key<key_type>{static_cast<key_type>(ek)};
+    if constexpr (is_map) {
+      auto const eval = cuco::empty_value<payload_t>{static_cast<payload_t>(ev)};
+      if (has_erased) {
+        return container_t{extent, ekey, eval, cuco::erased_key<key_type>{static_cast<key_type>(erased)},
+                           {}, {}, {}, {}, {}, sref(s)};
+      }
+      if (lf > 0.0 || lf < 0.0) { return container_t{extent, lf, ekey, eval, {}, {}, {}, {}, {}, sref(s)}; }
+      return container_t{extent, ekey, eval, {}, {}, {}, {}, {}, sref(s)};
+    } else {
+      (void)ev;
+      if (has_erased) {
+        return container_t{extent, ekey, cuco::erased_key<key_type>{static_cast<key_type>(erased)},
+                           {}, {}, {}, {}, {}, sref(s)};
+      }
+      if (lf > 0.0 || lf < 0.0) { return container_t{extent, lf, ekey, {}, {}, {}, {}, {}, sref(s)}; }
+      return container_t{extent, ekey, {}, {}, {}, {}, {}, sref(s)};
+    }
+  }
+
+  /// Presents the caller's buffers as the [first, last) range the container expects.
+  template <typename F>
+  void with_input(const void* keys, const void* values, i64 n, F&& f)
+  {
+    if constexpr (is_map) {
+      if (values == nullptr) {
+        auto const* p = static_cast<slot_type const*>(keys);  // AoS cuco::pair<Key,T>
+        f(p, p + n);
+      } else {
+        auto const zip = zip_to_pair<key_type, payload_t>{static_cast<key_type const*>(keys),
+                                                          static_cast<payload_t const*>(values)};
+        auto const first =
+          thrust::make_transform_iterator(thrust::counting_iterator<std::int64_t>{0}, zip);
+        f(first, first + n);
+      }
+    } else {
+      auto const* k = static_cast<key_type const*>(keys);
+      f(k, k + n);
+    }
+  }
+
+  container_t c_;
+};
+
+}  // namespace
+
+#define CUCO_SHIM_CAT2(a, b) a##b
+#define CUCO_SHIM_CAT(a, b)  CUCO_SHIM_CAT2(a, b)
+
+cuco_b200_table* CUCO_SHIM_CAT(cuco_shim_make_kind_, CUCO_SHIM_KIND)(std::int64_t size,
+                                                                      double load_factor,
+                                                                      std::int64_t empty_key,
+                                                                      std::int64_t empty_value,
+                                                                      int has_erased,
+                                                                      std::int64_t erased_key,
+                                                                      void* stream)
+{
+  return new table_impl<selected_container>(size, load_factor, empty_key, empty_value, has_erased, erased_key, stream);
+}

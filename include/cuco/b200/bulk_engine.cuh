@@ -1,0 +1,744 @@
+// table_engine — host side of the hot path: owns the slot storage and launches the bulk kernels.
+//
+// Counterpart of the reference's `detail::open_addressing_impl`
+// (include/cuco/detail/open_addressing/open_addressing_impl.cuh:69-1168) plus the map-only
+// launchers (detail/static_map/static_map.inl:279-358, detail/static_map/helpers.cuh:50-114).
+// Same stream-ordered contract: `*_async` never synchronise, the counting variants return after one
+// device->host copy. Differences in how the work is issued:
+//   * persistent grids sized to the resident-CTA count of the 148 SMs, several keys per thread,
+//     instead of one 128-thread block per 128/cg_size keys;
+//   * contiguous iterators are unwrapped to raw pointers so inputs stream through 128-bit
+//     non-allocating loads;
+//   * the success counter of the synchronous insert lives with the container (the reference
+//     cudaMallocs and frees one per call, impl.cuh:337-347);
+//   * tables small enough to live in L2 get an access-policy window on the launch (persisting
+//     lines for the table, streaming for everything else).
+// Run-time tuning (keys per thread, CAS-first, chunk width) is compiled in only when
+// CUCO_B200_TUNABLE is defined (the C-ABI library used by bench.py does); otherwise the defaults
+// below are the only instantiations.
+#pragma once
+
+#include <cuco/b200/bulk_kernels.cuh>
+#include <cuco/b200/probe_engine.cuh>
+#include <cuco/detail/error.hpp>
+#include <cuco/detail/utility/cuda.hpp>
+#include <cuco/detail/utils.hpp>
+#include <cuco/extent.cuh>
+#include <cuco/operator.hpp>
+#include <cuco/probing_scheme.cuh>
+#include <cuco/storage.cuh>
+
+#include <cuda/stream_ref>
+#include <thrust/iterator/constant_iterator.h>
+#include <thrust/type_traits/is_contiguous_iterator.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <type_traits>
+
+namespace cuco::b200 {
+
+/// Knobs of the bulk launchers. Defaults are what the header-only build uses.
+struct tuning_t {
+  int keys_per_thread  = 2;     ///< independent probes in flight per thread (1, 2 or 4)
+  bool cas_first       = true;  ///< inserts start with the CAS instead of a load
+  bool sector_chunks   = true;  ///< 32-byte chunk loads (else one window per load)
+  int waves            = 1;     ///< grid = waves * resident CTAs (persistent, grid-stride)
+  bool force_generic   = false; ///< route everything through the one-key-per-thread fallback
+  bool l2_window       = true;  ///< persisting-L2 access window for tables <= l2_window_bytes
+  std::size_t l2_window_bytes = std::size_t{48} << 20;
+};
+
+inline tuning_t tuning_from_env()
+{
+  tuning_t t{};
+  if (char const* s = std::getenv("CUCO_B200_KPT")) { t.keys_per_thread = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_CAS_FIRST")) { t.cas_first = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_SECTOR")) { t.sector_chunks = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_WAVES")) { t.waves = std::max(1, std::atoi(s)); }
+  if (char const* s = std::getenv("CUCO_B200_GENERIC")) { t.force_generic = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_L2_WINDOW")) { t.l2_window = std::atoi(s) != 0; }
+  return t;
+}
+
+/// Process-wide tuning state (mutable so a harness can sweep it between launches).
+inline tuning_t& tuning()
+{
+  static tuning_t t = tuning_from_env();
+  return t;
+}
+
+/// Identity predicate for the un-stencilled entry points.
+struct always_true {
+  template <typename T>
+  __host__ __device__ constexpr bool operator()(T const&) const noexcept
+  {
+    return true;
+  }
+};
+
+/// Grid for a persistent kernel: resident CTAs on the device times `waves`, capped by the tiles.
+template <typename Kernel>
+inline unsigned persistent_grid(Kernel kernel, int block_size, cuco::detail::index_type tiles)
+{
+  static int resident = 0;  // one per kernel instantiation; devices in a process are identical
+  if (resident == 0) { resident = cuco::detail::max_occupancy_grid_size(block_size, kernel); }
+  auto const want = static_cast<cuco::detail::index_type>(resident) * tuning().waves;
+  return static_cast<unsigned>(std::max<cuco::detail::index_type>(1, std::min(tiles, want)));
+}
+
+/// Launches `kernel` on `stream`; when `window_bytes` is non-zero the launch carries an L2 access
+/// policy window over [window_base, +window_bytes) marking those lines persisting.
+template <typename Kernel, typename... Args>
+inline void launch(Kernel kernel,
+                   unsigned grid,
+                   unsigned block,
+                   cudaStream_t stream,
+                   void* window_base,
+                   std::size_t window_bytes,
+                   Args... args)
+{
+  if (window_bytes == 0) {
+    kernel<<<grid, block, 0, stream>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t config{};
+  config.gridDim          = dim3{grid};
+  config.blockDim         = dim3{block};
+  config.dynamicSmemBytes = 0;
+  config.stream           = stream;
+  cudaLaunchAttribute attr{};
+  attr.id                                 = cudaLaunchAttributeAccessPolicyWindow;
+  attr.val.accessPolicyWindow.base_ptr    = window_base;
+  attr.val.accessPolicyWindow.num_bytes   = window_bytes;
+  attr.val.accessPolicyWindow.hitRatio    = 1.0f;
+  attr.val.accessPolicyWindow.hitProp     = cudaAccessPropertyPersisting;
+  attr.val.accessPolicyWindow.missProp    = cudaAccessPropertyStreaming;
+  config.attrs                            = &attr;
+  config.numAttrs                         = 1;
+  cudaLaunchKernelEx(&config, kernel, args...);
+}
+
+/// Makes sure the device has a persisting-L2 carve-out (once per process); returns its size.
+inline std::size_t persisting_l2_bytes()
+{
+  static std::size_t bytes = [] {
+    int dev = 0, max_persist = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { return std::size_t{0}; }
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (max_persist <= 0) { return std::size_t{0}; }
+    std::size_t current = 0;
+    cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
+    if (current == 0) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<std::size_t>(max_persist)) !=
+          cudaSuccess) {
+        cudaGetLastError();
+        return std::size_t{0};
+      }
+      current = static_cast<std::size_t>(max_persist);
+    }
+    return current;
+  }();
+  return bytes;
+}
+
+template <typename It>
+inline auto unwrap(It it)
+{
+  return thrust::try_unwrap_contiguous_iterator(it);
+}
+
+template <class Key,
+          class Value,
+          class Extent,
+          cuda::thread_scope Scope,
+          class KeyEqual,
+          class ProbingScheme,
+          class Allocator,
+          class Storage>
+class table_engine {
+  static_assert(sizeof(Key) <= 8, "Container does not support key types larger than 8 bytes.");
+  static_assert(sizeof(Value) <= 16, "Container does not support slot types larger than 16 bytes.");
+  static_assert(
+    cuco::is_bitwise_comparable_v<Key>,
+    "Key type must have unique object representations or have been explicitly declared as safe for "
+    "bitwise comparison via specialization of cuco::is_bitwise_comparable_v<Key>.");
+  static_assert(
+    std::is_base_of_v<cuco::detail::probing_scheme_base<ProbingScheme::cg_size>, ProbingScheme>,
+    "ProbingScheme must inherit from cuco::detail::probing_scheme_base");
+
+ public:
+  static constexpr auto has_payload  = !std::is_same_v<Key, Value>;
+  static constexpr auto cg_size      = ProbingScheme::cg_size;
+  static constexpr auto window_size  = Storage::window_size;
+  static constexpr auto thread_scope = Scope;
+
+  using key_type    = Key;
+  using value_type  = Value;  ///< slot type
+  using extent_type = decltype(make_window_extent<table_engine>(std::declval<Extent>()));
+  using size_type   = typename extent_type::value_type;
+  using key_equal   = KeyEqual;
+  using storage_type        = cuco::detail::storage<Storage, value_type, extent_type, Allocator>;
+  using allocator_type      = typename storage_type::allocator_type;
+  using storage_ref_type    = typename storage_type::ref_type;
+  using probing_scheme_type = ProbingScheme;
+  using hasher              = typename probing_scheme_type::hasher;
+  using engine_type =
+    probe_engine<key_type, Scope, key_equal, probing_scheme_type, storage_ref_type, false>;
+
+  static constexpr int block_size = 256;
+
+  // ------------------------------------------------------------------------------------------
+  // construction
+  // ------------------------------------------------------------------------------------------
+  constexpr table_engine(Extent capacity,
+                         Value empty_slot_sentinel,
+                         KeyEqual const& pred,
+                         ProbingScheme const& probing_scheme,
+                         Allocator const& alloc,
+                         cuda::stream_ref stream)
+    : empty_slot_sentinel_{empty_slot_sentinel},
+      erased_key_sentinel_{key_of(empty_slot_sentinel)},
+      predicate_{pred},
+      probing_scheme_{probing_scheme},
+      storage_{make_window_extent<table_engine>(capacity), alloc}
+  {
+    this->clear_async(stream);
+  }
+
+  constexpr table_engine(Extent n,
+                         double desired_load_factor,
+                         Value empty_slot_sentinel,
+                         KeyEqual const& pred,
+                         ProbingScheme const& probing_scheme,
+                         Allocator const& alloc,
+                         cuda::stream_ref stream)
+    : empty_slot_sentinel_{empty_slot_sentinel},
+      erased_key_sentinel_{key_of(empty_slot_sentinel)},
+      predicate_{pred},
+      probing_scheme_{probing_scheme},
+      storage_{make_window_extent<table_engine>(checked_capacity(n, desired_load_factor)), alloc}
+  {
+    this->clear_async(stream);
+  }
+
+  constexpr table_engine(Extent capacity,
+                         Value empty_slot_sentinel,
+                         Key erased_key_sentinel,
+                         KeyEqual const& pred,
+                         ProbingScheme const& probing_scheme,
+                         Allocator const& alloc,
+                         cuda::stream_ref stream)
+    : empty_slot_sentinel_{empty_slot_sentinel},
+      erased_key_sentinel_{erased_key_sentinel},
+      predicate_{pred},
+      probing_scheme_{probing_scheme},
+      storage_{make_window_extent<table_engine>(capacity), alloc}
+  {
+    CUCO_EXPECTS(this->empty_key_sentinel() != this->erased_key_sentinel(),
+                 "The empty key sentinel and erased key sentinel cannot be the same value.",
+                 std::logic_error);
+    this->clear_async(stream);
+  }
+
+  ~table_engine()
+  {
+    if (counter_ != nullptr) { cudaFree(counter_); }
+  }
+  table_engine(table_engine const&)            = delete;
+  table_engine& operator=(table_engine const&) = delete;
+
+  void clear(cuda::stream_ref stream) { storage_.initialize(empty_slot_sentinel_, stream); }
+  void clear_async(cuda::stream_ref stream) noexcept
+  {
+    storage_.initialize_async(empty_slot_sentinel_, stream);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // insert family
+  // ------------------------------------------------------------------------------------------
+  template <typename InputIt, typename Ref>
+  size_type insert(InputIt first, InputIt last, Ref ref, cuda::stream_ref stream)
+  {
+    return this->insert_if(
+      first, last, thrust::constant_iterator<bool>{true}, always_true{}, ref, stream);
+  }
+
+  template <typename InputIt, typename Ref>
+  void insert_async(InputIt first, InputIt last, Ref ref, cuda::stream_ref stream) noexcept
+  {
+    this->insert_if_async(
+      first, last, thrust::constant_iterator<bool>{true}, always_true{}, ref, stream);
+  }
+
+  template <typename InputIt, typename StencilIt, typename Predicate, typename Ref>
+  size_type insert_if(InputIt first,
+                      InputIt last,
+                      StencilIt stencil,
+                      Predicate pred,
+                      Ref ref,
+                      cuda::stream_ref stream)
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return 0; }
+    auto* counter = this->zeroed_counter(stream);
+    this->mutate<true>(first, n, stencil, pred, counter, ref, action_insert{}, stream);
+    return this->read_counter(stream);
+  }
+
+  template <typename InputIt, typename StencilIt, typename Predicate, typename Ref>
+  void insert_if_async(InputIt first,
+                       InputIt last,
+                       StencilIt stencil,
+                       Predicate pred,
+                       Ref ref,
+                       cuda::stream_ref stream) noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    this->mutate<false>(
+      first, n, stencil, pred, static_cast<size_type*>(nullptr), ref, action_insert{}, stream);
+  }
+
+  template <typename InputIt, typename FoundIt, typename InsertedIt, typename Ref>
+  void insert_and_find_async(InputIt first,
+                             InputIt last,
+                             FoundIt found_begin,
+                             InsertedIt inserted_begin,
+                             Ref ref,
+                             cuda::stream_ref stream) noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    auto found    = unwrap(found_begin);
+    auto inserted = unwrap(inserted_begin);
+    this->mutate<false>(first,
+                        n,
+                        thrust::constant_iterator<bool>{true},
+                        always_true{},
+                        static_cast<size_type*>(nullptr),
+                        ref,
+                        action_insert_and_find<decltype(found), decltype(inserted)>{found, inserted},
+                        stream);
+  }
+
+  template <typename InputIt, typename Ref>
+  void insert_or_assign_async(InputIt first, InputIt last, Ref ref, cuda::stream_ref stream) noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    this->mutate<false>(first,
+                        n,
+                        thrust::constant_iterator<bool>{true},
+                        always_true{},
+                        static_cast<size_type*>(nullptr),
+                        ref,
+                        action_assign{},
+                        stream);
+  }
+
+  /// `direct_apply`: the caller passed an init equal to the empty payload, so first arrivals combine
+  /// onto the sentinel instead of storing (decided on the host; same rule as
+  /// static_map_ref.inl:788-829 applies per element on the device).
+  template <typename InputIt, typename Op, typename Ref>
+  void insert_or_apply_async(
+    InputIt first, InputIt last, bool direct_apply, Op op, Ref ref, cuda::stream_ref stream) noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    auto const all = thrust::constant_iterator<bool>{true};
+    auto* no_count = static_cast<size_type*>(nullptr);
+    if (direct_apply) {
+      this->mutate<false>(
+        first, n, all, always_true{}, no_count, ref, action_apply<Op, true>{op}, stream);
+    } else {
+      this->mutate<false>(
+        first, n, all, always_true{}, no_count, ref, action_apply<Op, false>{op}, stream);
+    }
+  }
+
+  template <typename InputIt, typename Ref>
+  void erase_async(InputIt first, InputIt last, Ref ref, cuda::stream_ref stream = {})
+  {
+    CUCO_EXPECTS(this->empty_key_sentinel() != this->erased_key_sentinel(),
+                 "The empty key sentinel and erased key sentinel cannot be the same value.",
+                 std::logic_error);
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    auto in           = unwrap(first);
+    auto const engine = ref.engine();
+    auto const grid   = generic_grid(n);
+    erase_kernel<block_size><<<grid, block_size, 0, stream.get()>>>(in, n, engine);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // lookups
+  // ------------------------------------------------------------------------------------------
+  template <typename InputIt, typename OutputIt, typename Ref>
+  void contains_async(
+    InputIt first, InputIt last, OutputIt output_begin, Ref ref, cuda::stream_ref stream) const noexcept
+  {
+    this->contains_if_async(
+      first, last, thrust::constant_iterator<bool>{true}, always_true{}, output_begin, ref, stream);
+  }
+
+  template <typename InputIt,
+            typename StencilIt,
+            typename Predicate,
+            typename OutputIt,
+            typename Ref>
+  void contains_if_async(InputIt first,
+                         InputIt last,
+                         StencilIt stencil,
+                         Predicate pred,
+                         OutputIt output_begin,
+                         Ref ref,
+                         cuda::stream_ref stream) const noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    this->lookup(first, n, stencil, pred, output_begin, ref, emit_present{}, stream);
+  }
+
+  template <typename InputIt, typename OutputIt, typename Ref>
+  void find_async(
+    InputIt first, InputIt last, OutputIt output_begin, Ref ref, cuda::stream_ref stream) const noexcept
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return; }
+    this->lookup(first,
+                 n,
+                 thrust::constant_iterator<bool>{true},
+                 always_true{},
+                 output_begin,
+                 ref,
+                 emit_found<typename Ref::engine_type>{empty_slot_sentinel_},
+                 stream);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // whole-table queries
+  // ------------------------------------------------------------------------------------------
+  [[nodiscard]] size_type size(cuda::stream_ref stream) const
+  {
+    auto* counter     = this->zeroed_counter(stream);
+    auto const engine = this->make_engine();
+    auto const chunks = cuco::detail::int_div_ceil(
+      static_cast<cuco::detail::index_type>(storage_.capacity()),
+      cuco::detail::index_type{engine_type::sector_chunk_slots});
+    auto const kernel = size_kernel<block_size, engine_type, size_type>;
+    auto const grid   = persistent_grid(
+      kernel, block_size, cuco::detail::int_div_ceil(chunks, cuco::detail::index_type{block_size}));
+    kernel<<<grid, block_size, 0, stream.get()>>>(engine, counter);
+    return this->read_counter(stream);
+  }
+
+  [[nodiscard]] constexpr auto capacity() const noexcept { return storage_.capacity(); }
+  [[nodiscard]] constexpr key_type empty_key_sentinel() const noexcept
+  {
+    return key_of(empty_slot_sentinel_);
+  }
+  [[nodiscard]] constexpr value_type empty_slot_sentinel() const noexcept
+  {
+    return empty_slot_sentinel_;
+  }
+  [[nodiscard]] constexpr key_type erased_key_sentinel() const noexcept
+  {
+    return erased_key_sentinel_;
+  }
+  [[nodiscard]] constexpr key_equal key_eq() const noexcept { return predicate_; }
+  [[nodiscard]] constexpr probing_scheme_type const& probing_scheme() const noexcept
+  {
+    return probing_scheme_;
+  }
+  [[nodiscard]] constexpr hasher hash_function() const noexcept
+  {
+    return probing_scheme_.hash_function();
+  }
+  [[nodiscard]] constexpr allocator_type allocator() const noexcept { return storage_.allocator(); }
+  [[nodiscard]] constexpr storage_ref_type storage_ref() const noexcept { return storage_.ref(); }
+
+  /// Engine over the container's own storage (what the bulk kernels run on).
+  [[nodiscard]] engine_type make_engine() const noexcept
+  {
+    return engine_type{
+      empty_slot_sentinel_, erased_key_sentinel_, predicate_, probing_scheme_, storage_.ref()};
+  }
+
+  /// Minimal stand-in for a container ref when the engine is built from the table itself.
+  struct engine_handle {
+    using engine_type = typename table_engine::engine_type;
+    engine_type e;
+    [[nodiscard]] __host__ __device__ engine_type const& engine() const noexcept { return e; }
+  };
+
+  /// insert_if over the table's current storage without going through a container ref (rehash).
+  template <typename InputIt, typename StencilIt, typename Predicate>
+  void insert_slots_if(
+    InputIt first, InputIt last, StencilIt stencil, Predicate pred, cuda::stream_ref stream) noexcept
+  {
+    this->insert_if_async(first, last, stencil, pred, engine_handle{this->make_engine()}, stream);
+  }
+
+  /// Replaces the storage by a fresh one of `extent` windows; returns the old storage.
+  storage_type exchange_storage(extent_type extent, cuda::stream_ref stream)
+  {
+    storage_type old = std::move(storage_);
+    new (&storage_) storage_type{extent, old.allocator()};
+    this->clear_async(stream);
+    return old;
+  }
+
+ private:
+  [[nodiscard]] static constexpr key_type const& key_of(value_type const& slot) noexcept
+  {
+    if constexpr (has_payload) {
+      return slot.first;
+    } else {
+      return slot;
+    }
+  }
+
+  static Extent checked_capacity(Extent n, double desired_load_factor)
+  {
+    CUCO_EXPECTS(desired_load_factor > 0., "Desired occupancy must be larger than zero");
+    CUCO_EXPECTS(desired_load_factor <= 1., "Desired occupancy must be no larger than one");
+    // `Extent` may be a cuco::extent or a plain integer (CTAD from `static_map{n, ...}`)
+    using raw_size = typename extent_type::value_type;
+    return Extent{static_cast<raw_size>(
+      std::ceil(static_cast<double>(static_cast<raw_size>(n)) / desired_load_factor))};
+  }
+
+  static unsigned generic_grid(cuco::detail::index_type n)
+  {
+    auto const blocks = cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size});
+    auto const cap    = static_cast<cuco::detail::index_type>(cuco::detail::multiprocessor_count()) * 16;
+    return static_cast<unsigned>(std::max<cuco::detail::index_type>(1, std::min(blocks, cap)));
+  }
+
+  /// Can the sector-chunk, single-CAS kernels run on this table right now?
+  [[nodiscard]] bool fast_path_ok(bool mutating) const noexcept
+  {
+    if (tuning().force_generic) { return false; }
+    if (!engine_type::pow2_slot) { return false; }
+    if ((reinterpret_cast<std::uintptr_t>(storage_.data()) % 32) != 0) { return false; }
+    if (mutating) {
+      if (!engine_type::single_cas) { return false; }
+      if (!same_bits(erased_key_sentinel_, key_of(empty_slot_sentinel_))) { return false; }
+    }
+    return true;
+  }
+
+  /// Bytes of L2 window to request for this table (0 = none).
+  [[nodiscard]] std::size_t window_bytes() const noexcept
+  {
+    auto const bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
+    if (!tuning().l2_window || bytes > tuning().l2_window_bytes) { return 0; }
+    auto const carve_out = persisting_l2_bytes();
+    return bytes <= carve_out ? bytes : 0;
+  }
+
+  template <typename InputIt,
+            typename StencilIt,
+            typename Predicate,
+            typename OutputIt,
+            typename Ref,
+            typename Emit>
+  void lookup(InputIt first,
+              cuco::detail::index_type n,
+              StencilIt stencil,
+              Predicate pred,
+              OutputIt output_begin,
+              Ref ref,
+              Emit emit,
+              cuda::stream_ref stream) const noexcept
+  {
+    auto in           = unwrap(first);
+    auto st           = unwrap(stencil);
+    auto out          = unwrap(output_begin);
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    void* base        = storage_.data();
+    auto const window = this->window_bytes();
+
+    if (!this->fast_path_ok(false)) {
+      auto const kernel = generic_lookup_kernel<block_size,
+                                                decltype(in),
+                                                decltype(st),
+                                                Predicate,
+                                                decltype(out),
+                                                engine_t,
+                                                Emit>;
+      launch(kernel, generic_grid(n), block_size, stream.get(), base, window, in, n, st, pred, out, engine, emit);
+      return;
+    }
+
+    auto run = [&](auto kpt, auto chunk) {
+      constexpr int KPT   = decltype(kpt)::value;
+      constexpr int Chunk = decltype(chunk)::value;
+      auto const kernel   = lookup_kernel<block_size,
+                                        KPT,
+                                        Chunk,
+                                        decltype(in),
+                                        decltype(st),
+                                        Predicate,
+                                        decltype(out),
+                                        engine_t,
+                                        Emit>;
+      auto const tiles =
+        cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size} * KPT);
+      launch(kernel,
+             persistent_grid(kernel, block_size, tiles),
+             block_size,
+             stream.get(),
+             base,
+             window,
+             in,
+             n,
+             st,
+             pred,
+             out,
+             engine,
+             emit);
+    };
+    dispatch_variant<engine_t>(run);
+  }
+
+  template <bool Counted,
+            typename InputIt,
+            typename StencilIt,
+            typename Predicate,
+            typename Ref,
+            typename Action>
+  void mutate(InputIt first,
+              cuco::detail::index_type n,
+              StencilIt stencil,
+              Predicate pred,
+              size_type* counter,
+              Ref ref,
+              Action action,
+              cuda::stream_ref stream) noexcept
+  {
+    auto in           = unwrap(first);
+    auto st           = unwrap(stencil);
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    void* base        = storage_.data();
+    auto const window = this->window_bytes();
+
+    if constexpr (engine_t::single_cas && engine_t::pow2_slot) {
+      if (this->fast_path_ok(true)) {
+        auto run = [&](auto kpt, auto chunk) {
+          constexpr int KPT   = decltype(kpt)::value;
+          constexpr int Chunk = decltype(chunk)::value;
+          auto go             = [&](auto cas_first) {
+            constexpr bool CasFirst = decltype(cas_first)::value;
+            auto const kernel       = mutate_kernel<block_size,
+                                              KPT,
+                                              Chunk,
+                                              CasFirst,
+                                              Counted,
+                                              decltype(in),
+                                              decltype(st),
+                                              Predicate,
+                                              size_type,
+                                              engine_t,
+                                              Action>;
+            auto const tiles =
+              cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size} * KPT);
+            launch(kernel,
+                   persistent_grid(kernel, block_size, tiles),
+                   block_size,
+                   stream.get(),
+                   base,
+                   window,
+                   in,
+                   n,
+                   st,
+                   pred,
+                   counter,
+                   engine,
+                   action);
+          };
+#if defined(CUCO_B200_TUNABLE)
+          if (tuning().cas_first) {
+            go(std::true_type{});
+          } else {
+            go(std::false_type{});
+          }
+#else
+          go(std::true_type{});
+#endif
+        };
+        dispatch_variant<engine_t>(run);
+        return;
+      }
+    }
+    auto const kernel = generic_mutate_kernel<block_size,
+                                              Counted,
+                                              decltype(in),
+                                              decltype(st),
+                                              Predicate,
+                                              size_type,
+                                              engine_t,
+                                              Action>;
+    launch(kernel, generic_grid(n), block_size, stream.get(), base, window, in, n, st, pred, counter, engine, action);
+  }
+
+  /// Picks the (keys per thread, chunk width) instantiation.
+  template <typename EngineT, typename Run>
+  static void dispatch_variant(Run&& run)
+  {
+    constexpr int sector = EngineT::sector_chunk_slots;
+#if defined(CUCO_B200_TUNABLE)
+    constexpr int window = EngineT::window_chunk_slots;
+    auto const& t        = tuning();
+    auto with_chunk      = [&](auto kpt) {
+      if (t.sector_chunks || window == sector) {
+        run(kpt, std::integral_constant<int, sector>{});
+      } else {
+        run(kpt, std::integral_constant<int, window>{});
+      }
+    };
+    switch (t.keys_per_thread) {
+      case 1: with_chunk(std::integral_constant<int, 1>{}); break;
+      case 4: with_chunk(std::integral_constant<int, 4>{}); break;
+      default: with_chunk(std::integral_constant<int, 2>{}); break;
+    }
+#else
+    run(std::integral_constant<int, 2>{}, std::integral_constant<int, sector>{});
+#endif
+  }
+
+  /// Device counter owned by the container, zeroed on `stream`.
+  size_type* zeroed_counter(cuda::stream_ref stream) const
+  {
+    if (counter_ == nullptr) {
+      CUCO_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&counter_), sizeof(size_type)));
+    }
+    CUCO_CUDA_TRY(cudaMemsetAsync(counter_, 0, sizeof(size_type), stream.get()));
+    return counter_;
+  }
+
+  size_type read_counter(cuda::stream_ref stream) const
+  {
+    size_type host{};
+    CUCO_CUDA_TRY(
+      cudaMemcpyAsync(&host, counter_, sizeof(size_type), cudaMemcpyDeviceToHost, stream.get()));
+    stream.wait();
+    return host;
+  }
+
+ protected:
+  value_type empty_slot_sentinel_;
+  key_type erased_key_sentinel_;
+  key_equal predicate_;
+  probing_scheme_type probing_scheme_;
+  storage_type storage_;
+  mutable size_type* counter_{nullptr};
+};
+
+}  // namespace cuco::b200

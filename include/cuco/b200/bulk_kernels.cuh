@@ -1,0 +1,576 @@
+// Bulk kernels of the open-addressing hot path, written for sm_100a.
+//
+// They replace the reference's one-key-per-cooperative-group kernels
+// (include/cuco/detail/open_addressing/kernels.cuh:64-667 and detail/static_map/kernels.cuh:52-264:
+// insert_if_n, insert_and_find, find, contains_if_n, erase, size, insert_or_assign,
+// insert_or_apply). Design:
+//
+//  * thread-per-key, several keys per thread. A CTA takes a tile of BlockSize*KeysPerThread inputs;
+//    thread t owns inputs t, t+BlockSize, ... so every input load and output store of a warp is one
+//    contiguous segment. Each thread keeps KeysPerThread independent probe cursors and runs them in
+//    rounds: issue every pending chunk load (or slot CAS), then consume them all. The random-sector
+//    latency of one key is overlapped with the others' instead of being exposed per probe step.
+//  * the table is read in sector chunks: one 256-bit load brings the whole 32-byte DRAM sector the
+//    probe lands in (two 16-byte slots, four 8-byte, eight 4-byte) and is scanned from registers in
+//    probe order with early exit. Lookups use the non-coherent path and do not allocate in L1;
+//    mutating kernels read through L2 (relaxed.gpu) so a retry always observes the competing write.
+//  * a slot is claimed with one CAS on the whole slot image (32/64/128 bit). With `CasFirst` the
+//    first probe of an insert is the CAS itself - no load - which is the common case at load
+//    factors <= 0.5 where the home slot is usually free.
+//  * the grid is persistent: min(#tiles, resident CTAs on all SMs), grid-stride over tiles.
+//
+// Kernels with `generic_` prefix are the one-key-per-thread fallbacks used when the fast path's
+// preconditions do not hold (tombstones configured, padded slots, storage not 32-byte aligned).
+#pragma once
+
+#include <cuco/b200/probe_engine.cuh>
+#include <cuco/detail/utility/cuda.cuh>
+
+#include <cuda/atomic>
+#include <cuda/std/iterator>
+#include <thrust/iterator/iterator_traits.h>
+
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
+#include <cstdint>
+
+namespace cuco::b200 {
+
+using cuco::detail::index_type;
+
+/// Reads element `i` of an input range; raw pointers take the streaming (read-once) path.
+template <typename It>
+__device__ __forceinline__ auto read_input(It first, index_type i)
+{
+  using value_t = typename cuda::std::iterator_traits<It>::value_type;
+  if constexpr (cuda::std::is_pointer_v<It>) {
+    return load_streaming<cuda::std::remove_cv_t<value_t>>(first + i);
+  } else {
+    return static_cast<value_t>(*(first + i));
+  }
+}
+
+/// Adds a per-thread count into a global counter: warp shuffle reduce, one atomic per warp.
+template <typename Counter>
+__device__ __forceinline__ void accumulate_count(Counter* counter, unsigned long long mine)
+{
+  auto const warp = cg::tiled_partition<32>(cg::this_thread_block());
+  auto const sum  = cg::reduce(warp, mine, cg::plus<unsigned long long>());
+  if (warp.thread_rank() == 0 && sum != 0) {
+    cuda::atomic_ref<Counter, cuda::thread_scope_device> ref{*counter};
+    ref.fetch_add(static_cast<Counter>(sum), cuda::memory_order_relaxed);
+  }
+}
+
+// =================================================================================================
+// lookups: find / contains / contains_if
+// =================================================================================================
+
+/// Output policy of `find`: payload (map) or stored key (set), sentinel on a miss
+/// (reference: open_addressing/kernels.cuh:358-372).
+template <typename Engine>
+struct emit_found {
+  using slot_type = typename Engine::value_type;
+  slot_type empty_slot;
+
+  __device__ auto hit(slot_type const& slot) const noexcept
+  {
+    if constexpr (Engine::has_payload) {
+      return slot.second;
+    } else {
+      return slot;
+    }
+  }
+  __device__ auto miss() const noexcept { return hit(empty_slot); }
+};
+
+/// Output policy of `contains`.
+struct emit_present {
+  template <typename Slot>
+  __device__ bool hit(Slot const&) const noexcept
+  {
+    return true;
+  }
+  __device__ bool miss() const noexcept { return false; }
+};
+
+template <int BlockSize,
+          int KeysPerThread,
+          int ChunkSlots,
+          typename InputIt,
+          typename StencilIt,
+          typename Predicate,
+          typename OutputIt,
+          typename Engine,
+          typename Emit>
+CUCO_KERNEL __launch_bounds__(BlockSize) void lookup_kernel(InputIt first,
+                                                            index_type n,
+                                                            StencilIt stencil,
+                                                            Predicate pred,
+                                                            OutputIt out,
+                                                            Engine engine,
+                                                            Emit emit)
+{
+  using slot_type  = typename Engine::value_type;
+  using cursor     = typename Engine::cursor;
+  using probe_type = decltype(read_input(first, index_type{0}));
+  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
+  constexpr auto policy     = load_policy::readonly;
+
+  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
+       tile_base += index_type{gridDim.x} * tile) {
+    probe_type key[KeysPerThread];
+    cursor cur[KeysPerThread];
+    unsigned pending = 0;
+
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+      if (idx < n) {
+        if (pred(*(stencil + idx))) {
+          key[j] = read_input(first, idx);
+          cur[j] = engine.make_cursor(key[j]);
+          pending |= 1u << j;
+        } else {
+          *(out + idx) = emit.miss();
+        }
+      }
+    }
+
+    while (pending) {
+      raw_chunk<ChunkSlots * Engine::slot_bytes> raw[KeysPerThread];
+#pragma unroll
+      for (int j = 0; j < KeysPerThread; ++j) {
+        if (pending & (1u << j)) { raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]); }
+      }
+#pragma unroll
+      for (int j = 0; j < KeysPerThread; ++j) {
+        if (pending & (1u << j)) {
+          index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+          int const begin_off =
+            static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
+          int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
+          bool done       = false;
+#pragma unroll
+          for (int i = 0; i < ChunkSlots; ++i) {
+            if (!done && i >= begin_off && i < begin_off + valid) {
+              auto const slot  = chunk_slot<slot_type>(raw[j], i);
+              auto const state = engine.classify_lookup(key[j], Engine::key_of(slot));
+              if (state == equal_result::EQUAL) {
+                *(out + idx) = emit.hit(slot);
+                done         = true;
+              } else if (state == equal_result::EMPTY) {
+                *(out + idx) = emit.miss();
+                done         = true;
+              }
+            }
+          }
+          if (done) {
+            pending &= ~(1u << j);
+          } else {
+            engine.advance(cur[j], valid);
+          }
+        }
+      }
+    }
+  }
+}
+
+/// Fallback lookup: one key per thread through the engine's safe (window-chunk, plain load) path.
+template <int BlockSize,
+          typename InputIt,
+          typename StencilIt,
+          typename Predicate,
+          typename OutputIt,
+          typename Engine,
+          typename Emit>
+CUCO_KERNEL __launch_bounds__(BlockSize) void generic_lookup_kernel(InputIt first,
+                                                                    index_type n,
+                                                                    StencilIt stencil,
+                                                                    Predicate pred,
+                                                                    OutputIt out,
+                                                                    Engine engine,
+                                                                    Emit emit)
+{
+  for (index_type idx = cuco::detail::global_thread_id(); idx < n;
+       idx += cuco::detail::grid_stride()) {
+    if (pred(*(stencil + idx))) {
+      auto const key = read_input(first, idx);
+      auto const it  = engine.scalar_find(key);
+      if (it == engine.end()) {
+        *(out + idx) = emit.miss();
+      } else {
+        *(out + idx) = emit.hit(*it);
+      }
+    } else {
+      *(out + idx) = emit.miss();
+    }
+  }
+}
+
+// =================================================================================================
+// mutations: insert / insert_if / insert_and_find / insert_or_assign / insert_or_apply
+// =================================================================================================
+
+/// What a mutation does once it knows whether the key was new. `Engine` gives the slot types.
+/// Every action sees: the input index, the slot address, the slot image now stored there.
+struct action_insert {
+  static constexpr bool key_then_apply = false;
+  template <typename Engine, typename Slot>
+  __device__ void on_new(Engine const&, index_type, Slot*, Slot const&) const noexcept
+  {
+  }
+  template <typename Engine, typename Slot>
+  __device__ void on_present(Engine const&, index_type, Slot*, Slot const&, Slot const&) const noexcept
+  {
+  }
+};
+
+/// insert_and_find: report the resident payload/key and whether this element created the entry
+/// (reference: open_addressing/kernels.cuh:504-564).
+template <typename FoundIt, typename InsertedIt>
+struct action_insert_and_find {
+  static constexpr bool key_then_apply = false;
+  FoundIt found;
+  InsertedIt inserted;
+
+  template <typename Engine, typename Slot>
+  __device__ void emit(Engine const& engine, index_type idx, Slot* address, Slot image, bool is_new) const
+  {
+    if constexpr (Engine::has_payload) {
+      if (!is_new && same_bits(image.second, engine.empty_slot_sentinel().second)) {
+        // written by a two-step writer that has not published the payload yet
+        engine.wait_for_payload(address->second, engine.empty_slot_sentinel().second);
+        image.second = address->second;
+      }
+      *(found + idx) = image.second;
+    } else {
+      *(found + idx) = image;
+    }
+    *(inserted + idx) = is_new;
+  }
+  template <typename Engine, typename Slot>
+  __device__ void on_new(Engine const& e, index_type idx, Slot* address, Slot const& desired) const
+  {
+    emit(e, idx, address, desired, true);
+  }
+  template <typename Engine, typename Slot>
+  __device__ void on_present(
+    Engine const& e, index_type idx, Slot* address, Slot const& resident, Slot const&) const
+  {
+    emit(e, idx, address, resident, false);
+  }
+};
+
+/// insert_or_assign: last writer wins (reference: static_map_ref.inl:486-620).
+struct action_assign {
+  static constexpr bool key_then_apply = false;
+  template <typename Engine, typename Slot>
+  __device__ void on_new(Engine const&, index_type, Slot*, Slot const&) const noexcept
+  {
+  }
+  template <typename Engine, typename Slot>
+  __device__ void on_present(
+    Engine const&, index_type, Slot* address, Slot const&, Slot const& desired) const noexcept
+  {
+    using mapped = decltype(address->second);
+    cuda::atomic_ref<mapped, Engine::thread_scope> ref{address->second};
+    ref.store(desired.second, cuda::memory_order_relaxed);
+  }
+};
+
+/// insert_or_apply: first arrival stores its value, later arrivals combine with `op`
+/// (reference: static_map_ref.inl:850-1052). With `DirectApply` on 16-byte slots the first arrival
+/// claims the key only and combines onto the sentinel payload, exactly like the reference does when
+/// `init == empty_value_sentinel`.
+template <typename Op, bool DirectApply>
+struct action_apply {
+  static constexpr bool key_then_apply = DirectApply;
+  Op op;
+
+  template <typename Engine, typename Slot>
+  __device__ void on_new(Engine const&, index_type, Slot* address, Slot const& desired) const
+  {
+    if constexpr (DirectApply && sizeof(Slot) > 8) {
+      using mapped = decltype(address->second);
+      op(cuda::atomic_ref<mapped, Engine::thread_scope>{address->second}, desired.second);
+    }
+  }
+  template <typename Engine, typename Slot>
+  __device__ void on_present(
+    Engine const&, index_type, Slot* address, Slot const&, Slot const& desired) const
+  {
+    using mapped = decltype(address->second);
+    op(cuda::atomic_ref<mapped, Engine::thread_scope>{address->second}, desired.second);
+  }
+};
+
+template <int BlockSize,
+          int KeysPerThread,
+          int ChunkSlots,
+          bool CasFirst,
+          bool Counted,
+          typename InputIt,
+          typename StencilIt,
+          typename Predicate,
+          typename Counter,
+          typename Engine,
+          typename Action>
+CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
+                                                            index_type n,
+                                                            StencilIt stencil,
+                                                            Predicate pred,
+                                                            Counter* num_new,
+                                                            Engine engine,
+                                                            Action action)
+{
+  using slot_type = typename Engine::value_type;
+  using key_type  = typename Engine::key_type;
+  using cursor    = typename Engine::cursor;
+  // inputs stay in their own (possibly heterogeneous) type: hashing and the key predicate are
+  // invoked on it, exactly where the reference invokes them; the slot image is derived on demand
+  using input_type = decltype(engine.heterogeneous_value(read_input(first, index_type{0})));
+  static_assert(Engine::single_cas, "fast mutate path needs one-shot claimable slots");
+  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
+  constexpr auto policy     = load_policy::coherent;
+  // claim only the key half, then combine the payload in place (insert_or_apply direct mode)
+  constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
+
+  auto* const table      = engine.slots();
+  auto const empty_slot  = engine.empty_slot_sentinel();
+  unsigned long long mine = 0;
+
+  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
+       tile_base += index_type{gridDim.x} * tile) {
+    input_type val[KeysPerThread];
+    cursor cur[KeysPerThread];
+    unsigned pending = 0;  // bit j: key j still in flight
+    unsigned claim   = 0;  // bit j: next action of key j is a CAS at cur[j].slot (else a chunk load)
+
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+      if (idx < n && pred(*(stencil + idx))) {
+        val[j] = engine.heterogeneous_value(read_input(first, idx));
+        cur[j] = engine.make_cursor(Engine::key_of(val[j]));
+        pending |= 1u << j;
+        if constexpr (CasFirst) { claim |= 1u << j; }
+      }
+    }
+
+    while (pending) {
+      raw_chunk<ChunkSlots * Engine::slot_bytes> raw[KeysPerThread];
+      slot_type seen[KeysPerThread];
+
+      // ---- issue: every pending key posts its next memory operation ----
+#pragma unroll
+      for (int j = 0; j < KeysPerThread; ++j) {
+        if (pending & (1u << j)) {
+          if (claim & (1u << j)) {
+            if constexpr (key_only_claim) {
+              key_type expected_key = Engine::key_of(empty_slot);
+              cuda::atomic_ref<key_type, Engine::thread_scope> key_ref{(table + cur[j].slot)->first};
+              key_ref.compare_exchange_strong(expected_key,
+                                              static_cast<key_type>(Engine::key_of(val[j])),
+                                              cuda::memory_order_relaxed);
+              seen[j]       = empty_slot;
+              seen[j].first = expected_key;
+            } else {
+              seen[j] = cas_slot<Engine::thread_scope>(
+                table + cur[j].slot, empty_slot, engine.native_value(val[j]));
+            }
+          } else {
+            raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]);
+          }
+        }
+      }
+
+      // ---- consume ----
+#pragma unroll
+      for (int j = 0; j < KeysPerThread; ++j) {
+        if (!(pending & (1u << j))) { continue; }
+        index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+        auto const& key      = Engine::key_of(val[j]);
+        auto const desired   = engine.native_value(val[j]);
+
+        if (claim & (1u << j)) {
+          auto* const address = table + cur[j].slot;
+          bool const won      = key_only_claim
+                                  ? same_bits(Engine::key_of(seen[j]), Engine::key_of(empty_slot))
+                                  : same_bits(seen[j], empty_slot);
+          if (won) {
+            action.on_new(engine, idx, address, desired);
+            ++mine;
+            pending &= ~(1u << j);
+          } else {
+            auto const state = engine.classify_insert(key, Engine::key_of(seen[j]));
+            if (state == equal_result::EQUAL) {
+              action.on_present(engine, idx, address, seen[j], desired);
+              pending &= ~(1u << j);
+            } else if (state == equal_result::AVAILABLE) {
+              // still claimable but not bit-identical to the empty image (foreign payload):
+              // leave it to the general driver, which compares against what it observes
+              auto const res = engine.template insert_driver<ChunkSlots, policy>(
+                val[j], [&](slot_type* t, slot_type& e, auto const&) {
+                  return engine.try_claim(t, e, desired);
+                });
+              if (res.second) {
+                action.on_new(engine, idx, res.first, desired);
+                ++mine;
+              } else {
+                action.on_present(engine, idx, res.first, *res.first, desired);
+              }
+              pending &= ~(1u << j);
+            } else {
+              // somebody else's key lives here now: move on, next round loads
+              engine.advance(cur[j], 1);
+              claim &= ~(1u << j);
+            }
+          }
+        } else {
+          int const begin_off =
+            static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
+          int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
+          int consumed    = valid;
+          bool resolved   = false;
+#pragma unroll
+          for (int i = 0; i < ChunkSlots; ++i) {
+            if (!resolved && consumed == valid && i >= begin_off && i < begin_off + valid) {
+              auto const slot  = chunk_slot<slot_type>(raw[j], i);
+              auto const state = engine.classify_insert(key, Engine::key_of(slot));
+              if (state == equal_result::EQUAL) {
+                action.on_present(engine, idx, table + (cur[j].slot + (i - begin_off)), slot, desired);
+                resolved = true;
+              } else if (state == equal_result::AVAILABLE) {
+                consumed = i - begin_off;  // stop in front of this slot and claim it next round
+              }
+            }
+          }
+          if (resolved) {
+            pending &= ~(1u << j);
+          } else {
+            if (consumed < valid) { claim |= 1u << j; }
+            if (consumed > 0) { engine.advance(cur[j], consumed); }
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (Counted) { accumulate_count(num_new, mine); }
+}
+
+/// Fallback mutation: one key per thread through the engine's general drivers (tombstone aware,
+/// two-step claims for padded slots).
+template <int BlockSize,
+          bool Counted,
+          typename InputIt,
+          typename StencilIt,
+          typename Predicate,
+          typename Counter,
+          typename Engine,
+          typename Action>
+CUCO_KERNEL __launch_bounds__(BlockSize) void generic_mutate_kernel(InputIt first,
+                                                                    index_type n,
+                                                                    StencilIt stencil,
+                                                                    Predicate pred,
+                                                                    Counter* num_new,
+                                                                    Engine engine,
+                                                                    Action action)
+{
+  using slot_type = typename Engine::value_type;
+  using key_type  = typename Engine::key_type;
+  unsigned long long mine = 0;
+
+  for (index_type idx = cuco::detail::global_thread_id(); idx < n;
+       idx += cuco::detail::grid_stride()) {
+    if (!pred(*(stencil + idx))) { continue; }
+    auto const val     = engine.heterogeneous_value(read_input(first, idx));
+    auto const desired = engine.native_value(val);
+    constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
+
+    auto const res = engine.template insert_driver<Engine::window_chunk_slots, load_policy::plain>(
+      val, [&](slot_type* target, slot_type& expected, auto const&) {
+        if constexpr (key_only_claim) {
+          key_type expected_key = Engine::key_of(expected);
+          auto const r          = engine.try_claim_key(target, expected_key, desired.first);
+          expected.first        = expected_key;
+          return r;
+        } else {
+          return engine.try_claim(target, expected, desired);
+        }
+      });
+    if (res.second) {
+      action.on_new(engine, idx, res.first, desired);
+      ++mine;
+    } else {
+      if constexpr (Engine::has_payload && !cuda::std::is_same_v<Action, action_insert>) {
+        // two-step writers publish the payload after the key: wait before reading or combining,
+        // unless the first arrival itself combines onto the sentinel (direct apply)
+        if constexpr (!key_only_claim && !Engine::single_cas) {
+          if constexpr (!cuda::std::is_same_v<Action, action_assign>) {
+            engine.wait_for_payload(res.first->second, engine.empty_slot_sentinel().second);
+          }
+        }
+      }
+      action.on_present(engine, idx, res.first, *res.first, desired);
+    }
+  }
+
+  if constexpr (Counted) { accumulate_count(num_new, mine); }
+}
+
+// =================================================================================================
+// erase (tombstoning) - one key per thread
+// =================================================================================================
+template <int BlockSize, typename InputIt, typename Engine>
+CUCO_KERNEL __launch_bounds__(BlockSize) void erase_kernel(InputIt first, index_type n, Engine engine)
+{
+  for (index_type idx = cuco::detail::global_thread_id(); idx < n;
+       idx += cuco::detail::grid_stride()) {
+    engine.scalar_erase(read_input(first, idx));
+  }
+}
+
+// =================================================================================================
+// size: streaming count of filled slots (neither empty nor erased key)
+// =================================================================================================
+template <int BlockSize, typename Engine, typename Counter>
+CUCO_KERNEL __launch_bounds__(BlockSize) void size_kernel(Engine engine, Counter* count)
+{
+  using slot_type = typename Engine::value_type;
+  auto const* table = engine.slots();
+  auto const n      = static_cast<index_type>(engine.capacity());
+  auto const empty  = engine.empty_key_sentinel();
+  auto const erased = engine.erased_key_sentinel();
+  unsigned long long mine = 0;
+
+  constexpr int chunk = Engine::sector_chunk_slots;
+  bool const vector_ok = (reinterpret_cast<std::uintptr_t>(table) % 32) == 0;
+  if (chunk > 1 && vector_ok) {
+    // whole sectors; the allocation is padded so the last chunk may be read in full
+    index_type const chunks = (n + chunk - 1) / chunk;
+    for (index_type c = cuco::detail::global_thread_id(); c < chunks;
+         c += cuco::detail::grid_stride()) {
+      auto const raw =
+        load_chunk_bytes<chunk * Engine::slot_bytes, load_policy::readonly>(table + c * chunk);
+#pragma unroll
+      for (int i = 0; i < chunk; ++i) {
+        if (c * chunk + i < n) {
+          auto const& k = Engine::key_of(chunk_slot<slot_type>(raw, i));
+          mine += !(same_bits(k, empty) || same_bits(k, erased));
+        }
+      }
+    }
+  } else {
+    for (index_type i = cuco::detail::global_thread_id(); i < n;
+         i += cuco::detail::grid_stride()) {
+      auto const& k = Engine::key_of(table[i]);
+      mine += !(same_bits(k, empty) || same_bits(k, erased));
+    }
+  }
+  accumulate_count(count, mine);
+}
+
+}  // namespace cuco::b200

@@ -1,0 +1,194 @@
+/* cuco_b200.h — C ABI of the b200-native open-addressing hash table.
+ *
+ * The reference (NVIDIA/cuCollections) is a header-only C++ template library with no FFI; its
+ * boundary for this path is the `cuco::static_map` / `cuco::static_set` class templates
+ * (reference include/cuco/static_map.cuh:88-986, include/cuco/static_set.cuh:82-798), which this
+ * repository re-implements under include/cuco/. This header is the plain-C view of explicit
+ * instantiations of that surface, so that non-C++ hosts (ctypes, cgo, JNI, ...) and the parity /
+ * benchmark harness can drive it. Every entry point names the reference member it forwards to.
+ *
+ * The same shim source (cucollections_b200/csrc/cabi_*.cu) is compiled twice:
+ *   libcuco_b200.so        against include/cuco           (this implementation)
+ *   oracle/_ref/libcuco_ref.so against /root/reference/include (cuco's own sm_100a build)
+ * so both run through identical glue and can be compared call for call.
+ *
+ * Conventions: all pointers are device pointers unless stated otherwise; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream); keys/values/sentinels are passed as
+ * int64_t and narrowed to the table's key/payload type; functions return 0 on success and a
+ * non-zero code otherwise, with a message available from cuco_b200_last_error() (thread local).
+ * "_async" behaviour: calls that do not return a count or size only enqueue work on `stream`.
+ */
+#ifndef CUCO_B200_H
+#define CUCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cuco_b200_table cuco_b200_table; /* opaque */
+
+/* Explicit instantiations. cg = cooperative-group size of the probing scheme (bucket width in
+ * windows), w = slots per window (cuco::storage<w>). Hash is cuco::default_hash_function
+ * (xxhash_32) unless noted. */
+enum cuco_b200_kind {
+  CUCO_B200_SET_I32_DH4       = 0, /* static_set<int32>            double_hashing<4> w1 (class default) */
+  CUCO_B200_MAP_I64_LP1       = 1, /* static_map<int64,int64>      linear_probing<1> w1 */
+  CUCO_B200_MAP_I64_DH8       = 2, /* static_map<int64,int64>      double_hashing<8> w1 */
+  CUCO_B200_MAP_I32_LP4       = 3, /* static_map<int32,int32>      linear_probing<4> w1 (class default) */
+  CUCO_B200_MAP_I64_LP4       = 4, /* static_map<int64,int64>      linear_probing<4> w1 (class default) */
+  CUCO_B200_SET_I64_DH4       = 5, /* static_set<int64>            double_hashing<4> w1 (class default) */
+  CUCO_B200_MAP_I64_LP1_W2    = 6, /* static_map<int64,int64>      linear_probing<1> w2 (window = 32 B sector) */
+  CUCO_B200_MAP_I32_DH2_W2_MM = 7, /* static_map<int32,int32>      double_hashing<2, murmurhash3_32> w2 (reference test matrix) */
+  CUCO_B200_MAP_I32I64_LP1    = 8, /* static_map<int32,int64>      linear_probing<1> w1 (padded 16 B slot: two-step claim path) */
+  CUCO_B200_MAP_I64_DH8_X64   = 9, /* static_map<int64,int64>      double_hashing<8, xxhash_64> w1 (tables near 2^32 windows) */
+  CUCO_B200_NUM_KINDS         = 10
+};
+
+/* Reduction selector for cuco_b200_insert_or_apply (cuco::reduce::plus / min / max,
+ * reference include/cuco/utility/reduction_functors.cuh:25-82). */
+enum cuco_b200_reduce_op { CUCO_B200_PLUS = 0, CUCO_B200_MIN = 1, CUCO_B200_MAX = 2 };
+
+/* "native" for this implementation, "reference" for the cuco build of the same shim. */
+const char* cuco_b200_build_info(void);
+const char* cuco_b200_last_error(void);
+
+/* Constructors (reference static_map.cuh:160-260 / static_set.cuh:148-240).
+ *   load_factor == 0 : `size` is a capacity           -> ctor(capacity, sentinels...)
+ *   load_factor  > 0 : `size` is a number of keys     -> ctor(n, desired_load_factor, sentinels...)
+ *   has_erased  != 0 : ctor(capacity, sentinels..., erased_key)  (load_factor must be 0)
+ * Errors: load factor outside (0,1], erased == empty, extent too large, allocation failure. */
+int cuco_b200_create(int kind,
+                     int64_t size,
+                     double load_factor,
+                     int64_t empty_key,
+                     int64_t empty_value,
+                     int has_erased,
+                     int64_t erased_key,
+                     void* stream,
+                     cuco_b200_table** out);
+int cuco_b200_destroy(cuco_b200_table* t);
+
+int cuco_b200_kind_of(const cuco_b200_table* t);
+int cuco_b200_key_bytes(const cuco_b200_table* t);   /* 4 or 8 */
+int cuco_b200_value_bytes(const cuco_b200_table* t); /* 0 for sets */
+int64_t cuco_b200_capacity(const cuco_b200_table* t); /* capacity()  */
+int cuco_b200_size(cuco_b200_table* t, void* stream, int64_t* out); /* size(stream), synchronises */
+int cuco_b200_clear(cuco_b200_table* t, void* stream);              /* clear_async(stream) */
+
+/* insert / insert_async (static_map.cuh:302,316; static_set.cuh:272,286).
+ * Maps: `values == NULL` means `keys` is an array of cuco::pair<Key,T> (AoS, the layout the
+ * reference benchmarks use); otherwise keys and values are separate arrays (exercises the generic
+ * iterator path through a transform iterator). Sets ignore `values`.
+ * `num_inserted == NULL` -> insert_async; else synchronous insert and *num_inserted (host) = #new keys. */
+int cuco_b200_insert(cuco_b200_table* t,
+                     const void* keys,
+                     const void* values,
+                     int64_t n,
+                     void* stream,
+                     int64_t* num_inserted);
+
+/* insert_if / insert_if_async with stencil of bytes, predicate "stencil[i] != 0"
+ * (static_map.cuh:344,373). */
+int cuco_b200_insert_if(cuco_b200_table* t,
+                        const void* keys,
+                        const void* values,
+                        const uint8_t* stencil,
+                        int64_t n,
+                        void* stream,
+                        int64_t* num_inserted);
+
+/* find_async (static_map.cuh:765; static_set.cuh:588): out[i] = payload (maps) / stored key (sets),
+ * or the empty value / empty key sentinel. `out` has the payload (maps) or key (sets) type. */
+int cuco_b200_find(cuco_b200_table* t, const void* keys, void* out, int64_t n, void* stream);
+
+/* contains_async (static_map.cuh:661; static_set.cuh:484): out[i] = 0/1 as bool bytes. */
+int cuco_b200_contains(cuco_b200_table* t, const void* keys, uint8_t* out, int64_t n, void* stream);
+
+/* contains_if_async (static_map.cuh:722): out[i] = stencil[i] != 0 ? contains(keys[i]) : false. */
+int cuco_b200_contains_if(cuco_b200_table* t,
+                          const void* keys,
+                          const uint8_t* stencil,
+                          uint8_t* out,
+                          int64_t n,
+                          void* stream);
+
+/* insert_and_find_async (static_map.cuh:395; static_set.cuh:365): found[i] = resident payload/key,
+ * inserted[i] = this element created the entry. `keys`/`values` as in cuco_b200_insert. */
+int cuco_b200_insert_and_find(cuco_b200_table* t,
+                              const void* keys,
+                              const void* values,
+                              void* found,
+                              uint8_t* inserted,
+                              int64_t n,
+                              void* stream);
+
+/* insert_or_assign_async (static_map.cuh:467). Maps only. */
+int cuco_b200_insert_or_assign(
+  cuco_b200_table* t, const void* keys, const void* values, int64_t n, void* stream);
+
+/* insert_or_apply_async (static_map.cuh:541 without init, :573 with init). Maps only. */
+int cuco_b200_insert_or_apply(cuco_b200_table* t,
+                              const void* keys,
+                              const void* values,
+                              int64_t n,
+                              int reduce_op,
+                              int has_init,
+                              int64_t init,
+                              void* stream);
+
+/* erase_async (static_map.cuh:620; static_set.cuh:449). Requires an erased-key sentinel. */
+int cuco_b200_erase(cuco_b200_table* t, const void* keys, int64_t n, void* stream);
+
+/* retrieve_all (static_map.cuh:893; static_set.cuh:682): unordered dump; *n_out (host) = count.
+ * `values_out` is ignored for sets. Outputs must hold `capacity` elements. Synchronises. */
+int cuco_b200_retrieve_all(
+  cuco_b200_table* t, void* keys_out, void* values_out, int64_t* n_out, void* stream);
+
+/* rehash (static_map.cuh:911,931): capacity < 0 keeps the current extent. Synchronises. */
+int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream);
+
+/* Launch tuning of the native build (no-op returning 1 in the reference build).
+ * keys_per_thread in {1,2,4}; the others are booleans; waves >= 1. Negative = leave unchanged. */
+int cuco_b200_set_tuning(
+  int keys_per_thread, int cas_first, int sector_chunks, int waves, int force_generic, int l2_window);
+
+/* ---- hash-partitioned multi-GPU support (no reference counterpart) --------------
+ * owner(key) = mulhi64(murmur_fmix64(key ^ salt), num_parts): high bits of a mix that is independent
+ * of the in-table hash. Both calls are stream-ordered and only enqueue work.
+ *
+ * cuco_b200_partition_count: counts[p] += #{i : owner(keys[i]) == p}   (counts: int64[num_parts], device)
+ * cuco_b200_partition_scatter: given exclusive offsets (device int64[num_parts], consumed as running
+ *   cursors), writes keys (and values if non-NULL, and the source index if src_index != NULL) of each
+ *   element into its owner's segment. key_bytes/value_bytes in {4,8}. pair_aos != 0: `keys` is an
+ *   array of {key,value} structs of 2*key_bytes and the output is the same AoS layout. */
+int cuco_b200_partition_count(const void* keys,
+                              int key_bytes,
+                              int pair_aos,
+                              int64_t n,
+                              int num_parts,
+                              uint64_t salt,
+                              int64_t* counts,
+                              void* stream);
+int cuco_b200_partition_scatter(const void* keys,
+                                const void* values,
+                                int key_bytes,
+                                int value_bytes,
+                                int pair_aos,
+                                int64_t n,
+                                int num_parts,
+                                uint64_t salt,
+                                int64_t* cursors,
+                                void* keys_out,
+                                void* values_out,
+                                int64_t* src_index,
+                                void* stream);
+/* out[index[i]] = in[i] for i < n (elem_bytes in {1,4,8}); un-permutes routed lookup results. */
+int cuco_b200_scatter_by_index(
+  const void* in, const int64_t* index, void* out, int elem_bytes, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUCO_B200_H */
