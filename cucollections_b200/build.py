@@ -38,7 +38,7 @@ COMMON = [
     "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
-    "-diag-suppress", "20012,20011,177",
+    "-diag-suppress", "20012,20011,177,1407",
 ]
 
 
@@ -89,8 +89,6 @@ def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], refe
             objs.append(obj)
             if verbose and secs:
                 print(f"  built {obj.name} in {secs:.1f}s", file=sys.stderr)
-            if verbose and err.strip():
-                print(err, file=sys.stderr)
     newest = max(o.stat().st_mtime for o in objs)
     if not lib.exists() or lib.stat().st_mtime < newest:
         cmd = [NVCC, "-shared", "-o", str(lib), *map(str, objs), "-lcudart"]

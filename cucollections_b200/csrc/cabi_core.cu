@@ -226,6 +226,8 @@ unsigned route_grid(std::int64_t n, std::int64_t per_block)
 
 }  // namespace
 
+// everything else in the library is built with -fvisibility=hidden; the C ABI is the export list
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char* cuco_b200_build_info(void)
@@ -549,3 +551,4 @@ int cuco_b200_scatter_by_index(
 }
 
 }  // extern "C"
+#pragma GCC visibility pop
