@@ -415,12 +415,17 @@ int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream)
   });
 }
 
-int cuco_b200_set_tuning(
-  int keys_per_thread, int cas_first, int sector_chunks, int waves, int force_generic, int l2_window)
+int cuco_b200_set_tuning(int keys_per_thread,
+                         int cas_first,
+                         int sector_chunks,
+                         int waves,
+                         int force_generic,
+                         int l2_window,
+                         int coherent_loads)
 {
 #if defined(CUCO_SHIM_REFERENCE)
   (void)keys_per_thread, (void)cas_first, (void)sector_chunks, (void)waves, (void)force_generic,
-    (void)l2_window;
+    (void)l2_window, (void)coherent_loads;
   return 1;
 #else
   auto& t = cuco::b200::tuning();
@@ -432,6 +437,20 @@ int cuco_b200_set_tuning(
   if (waves >= 1) { t.waves = waves; }
   if (force_generic >= 0) { t.force_generic = force_generic != 0; }
   if (l2_window >= 0) { t.l2_window = l2_window != 0; }
+  if (coherent_loads >= 0) { t.coherent_loads = coherent_loads != 0; }
+  return 0;
+#endif
+}
+
+int cuco_b200_set_blocking(int mode, int region_mib)
+{
+#if defined(CUCO_SHIM_REFERENCE)
+  (void)mode, (void)region_mib;
+  return 1;
+#else
+  auto& t   = cuco::b200::tuning();
+  t.blocked = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  if (region_mib > 0) { t.region_bytes = static_cast<std::size_t>(region_mib) << 20; }
   return 0;
 #endif
 }

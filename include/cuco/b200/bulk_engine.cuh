@@ -30,6 +30,7 @@
 
 #include <cuda/stream_ref>
 #include <thrust/iterator/constant_iterator.h>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/type_traits/is_contiguous_iterator.h>
 
 #include <cmath>
@@ -44,11 +45,17 @@ namespace cuco::b200 {
 /// Knobs of the bulk launchers. Defaults are what the header-only build uses.
 struct tuning_t {
   int keys_per_thread  = 2;     ///< independent probes in flight per thread (1, 2 or 4)
-  bool cas_first       = true;  ///< inserts start with the CAS instead of a load
+  bool cas_first       = false; ///< inserts start with the CAS instead of a load (pays off only
+                                ///< when nearly every key is new: a failed CAS still dirties the sector)
   bool sector_chunks   = true;  ///< 32-byte chunk loads (else one window per load)
   int waves            = 1;     ///< grid = waves * resident CTAs (persistent, grid-stride)
   bool force_generic   = false; ///< route everything through the one-key-per-thread fallback
   bool l2_window       = true;  ///< persisting-L2 access window for tables <= l2_window_bytes
+  bool coherent_loads  = false; ///< mutating kernels read the table with relaxed.gpu loads
+  int blocked          = -1;    ///< L2-blocked mutations: -1 auto (tables much larger than L2), 0 off, 1 on
+  std::size_t region_bytes          = std::size_t{32} << 20;   ///< table slice kept L2-resident
+  std::size_t blocked_min_table     = std::size_t{192} << 20;  ///< auto mode: table at least this big
+  std::int64_t blocked_min_elements = std::int64_t{1} << 22;   ///< auto mode: batch at least this big
   std::size_t l2_window_bytes = std::size_t{48} << 20;
 };
 
@@ -61,6 +68,11 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_WAVES")) { t.waves = std::max(1, std::atoi(s)); }
   if (char const* s = std::getenv("CUCO_B200_GENERIC")) { t.force_generic = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_L2_WINDOW")) { t.l2_window = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_COHERENT")) { t.coherent_loads = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_BLOCKED")) { t.blocked = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
+    t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
+  }
   return t;
 }
 
@@ -247,6 +259,7 @@ class table_engine {
   ~table_engine()
   {
     if (counter_ != nullptr) { cudaFree(counter_); }
+    if (scratch_ != nullptr) { cudaFree(scratch_); }
   }
   table_engine(table_engine const&)            = delete;
   table_engine& operator=(table_engine const&) = delete;
@@ -629,18 +642,29 @@ class table_engine {
     void* base        = storage_.data();
     auto const window = this->window_bytes();
 
+    if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable &&
+                  std::is_same_v<StencilIt, thrust::constant_iterator<bool>> &&
+                  std::is_same_v<Predicate, always_true>) {
+      if (this->fast_path_ok(true) && this->blocking_pays(n)) {
+        this->blocked_mutate<Counted>(in, n, counter, engine, action, stream);
+        return;
+      }
+    }
     if constexpr (engine_t::single_cas && engine_t::pow2_slot) {
       if (this->fast_path_ok(true)) {
         auto run = [&](auto kpt, auto chunk) {
           constexpr int KPT   = decltype(kpt)::value;
           constexpr int Chunk = decltype(chunk)::value;
-          auto go             = [&](auto cas_first) {
+          auto go             = [&](auto cas_first, auto coherent) {
             constexpr bool CasFirst = decltype(cas_first)::value;
-            auto const kernel       = mutate_kernel<block_size,
+            constexpr auto Policy =
+              decltype(coherent)::value ? load_policy::coherent : load_policy::streaming;
+            auto const kernel = mutate_kernel<block_size,
                                               KPT,
                                               Chunk,
                                               CasFirst,
                                               Counted,
+                                              Policy,
                                               decltype(in),
                                               decltype(st),
                                               Predicate,
@@ -664,13 +688,16 @@ class table_engine {
                    action);
           };
 #if defined(CUCO_B200_TUNABLE)
-          if (tuning().cas_first) {
-            go(std::true_type{});
+          auto const& t = tuning();
+          if (t.cas_first) {
+            t.coherent_loads ? go(std::true_type{}, std::true_type{})
+                             : go(std::true_type{}, std::false_type{});
           } else {
-            go(std::false_type{});
+            t.coherent_loads ? go(std::false_type{}, std::true_type{})
+                             : go(std::false_type{}, std::false_type{});
           }
 #else
-          go(std::true_type{});
+          go(std::false_type{}, std::false_type{});
 #endif
         };
         dispatch_variant<engine_t>(run);
@@ -686,6 +713,96 @@ class table_engine {
                                               engine_t,
                                               Action>;
     launch(kernel, generic_grid(n), block_size, stream.get(), base, window, in, n, st, pred, counter, engine, action);
+  }
+
+  /// Should this batch take the L2-blocked path?
+  [[nodiscard]] bool blocking_pays(cuco::detail::index_type n) const noexcept
+  {
+    auto const& t = tuning();
+    if (t.blocked == 0) { return false; }
+    if (t.blocked > 0) { return n > 0; }
+    auto const bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
+    return bytes >= t.blocked_min_table && n >= t.blocked_min_elements;
+  }
+
+  /// Grow-only staging memory owned by the container (avoids a malloc/free per bulk call).
+  void* scratch(std::size_t bytes)
+  {
+    if (bytes > scratch_bytes_) {
+      if (scratch_ != nullptr) { CUCO_CUDA_TRY(cudaFree(scratch_)); }
+      scratch_       = nullptr;
+      scratch_bytes_ = 0;
+      CUCO_CUDA_TRY(cudaMalloc(&scratch_, bytes));
+      scratch_bytes_ = bytes;
+    }
+    return scratch_;
+  }
+
+  /// L2-blocked mutation: route the batch by table region (pass 1), then run the ordinary mutate
+  /// kernel over the regions in order (pass 2). See bulk_kernels.cuh, "L2-blocked mutation".
+  template <bool Counted, typename InputIt, typename EngineT, typename Action>
+  void blocked_mutate(InputIt in,
+                      cuco::detail::index_type n,
+                      size_type* counter,
+                      EngineT const& engine,
+                      Action action,
+                      cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    auto const& t          = tuning();
+    auto const capacity    = static_cast<std::uint64_t>(storage_.capacity());
+    auto const table_bytes = capacity * sizeof(value_type);
+    auto const num_regions = static_cast<std::uint32_t>(std::min<std::uint64_t>(
+      route_max_regions, std::max<std::uint64_t>(2, (table_bytes + t.region_bytes - 1) / t.region_bytes)));
+    // expected elements per region plus 1/16 slack and a constant for tiny batches
+    auto const mean             = (static_cast<std::uint64_t>(n) + num_regions - 1) / num_regions;
+    auto const segment_capacity = static_cast<std::uint32_t>(mean + mean / 16 + 1024);
+    auto const virtual_n        = static_cast<index_type>(num_regions) * segment_capacity;
+
+    std::size_t const counts_bytes = ((num_regions * sizeof(unsigned int)) + 255) / 256 * 256;
+    auto* base     = static_cast<char*>(this->scratch(counts_bytes + virtual_n * sizeof(value_type)));
+    auto* counts   = reinterpret_cast<unsigned int*>(base);
+    auto* segments = reinterpret_cast<value_type*>(base + counts_bytes);
+    cudaMemsetAsync(counts, 0, num_regions * sizeof(unsigned int), stream.get());
+
+    unsigned __int128 const scaled = (static_cast<unsigned __int128>(num_regions) << 64) / capacity;
+    region_map const regions{static_cast<std::uint64_t>(scaled) + 1, num_regions};
+
+    constexpr int chunk = EngineT::sector_chunk_slots;
+    {
+      auto const kernel  = route_kernel<block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
+      auto const tiles   = cuco::detail::int_div_ceil(n, index_type{block_size} * route_items_per_thread);
+      std::size_t const smem = 2 * num_regions * sizeof(unsigned int);
+      auto const grid = static_cast<unsigned>(
+        std::min<index_type>(tiles, index_type{cuco::detail::multiprocessor_count()} * 4));
+      kernel<<<grid, block_size, smem, stream.get()>>>(
+        in, n, segments, counts, regions, segment_capacity, counter, engine, action);
+    }
+    {
+      auto const stencil = thrust::counting_iterator<index_type>{0};
+      auto const live    = segment_live{counts, segment_capacity};
+      auto const* first  = static_cast<value_type const*>(segments);
+      auto run           = [&](auto kpt, auto chunk_tag) {
+        constexpr int KPT   = decltype(kpt)::value;
+        constexpr int Chunk = decltype(chunk_tag)::value;
+        auto const kernel   = mutate_kernel<block_size,
+                                          KPT,
+                                          Chunk,
+                                          false,
+                                          Counted,
+                                          load_policy::streaming,
+                                          value_type const*,
+                                          thrust::counting_iterator<index_type>,
+                                          segment_live,
+                                          size_type,
+                                          EngineT,
+                                          Action>;
+        auto const tiles = cuco::detail::int_div_ceil(virtual_n, index_type{block_size} * KPT);
+        kernel<<<persistent_grid(kernel, block_size, tiles), block_size, 0, stream.get()>>>(
+          first, virtual_n, stencil, live, counter, engine, action);
+      };
+      dispatch_variant<EngineT>(run);
+    }
   }
 
   /// Picks the (keys per thread, chunk width) instantiation.
@@ -739,6 +856,8 @@ class table_engine {
   probing_scheme_type probing_scheme_;
   storage_type storage_;
   mutable size_type* counter_{nullptr};
+  void* scratch_{nullptr};          ///< grow-only staging buffer of the blocked path
+  std::size_t scratch_bytes_{0};
 };
 
 }  // namespace cuco::b200

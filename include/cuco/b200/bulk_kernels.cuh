@@ -217,6 +217,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void generic_lookup_kernel(InputIt firs
 /// Every action sees: the input index, the slot address, the slot image now stored there.
 struct action_insert {
   static constexpr bool key_then_apply = false;
+  static constexpr bool blockable      = true;  ///< no per-element output: input order is free
   template <typename Engine, typename Slot>
   __device__ void on_new(Engine const&, index_type, Slot*, Slot const&) const noexcept
   {
@@ -232,6 +233,7 @@ struct action_insert {
 template <typename FoundIt, typename InsertedIt>
 struct action_insert_and_find {
   static constexpr bool key_then_apply = false;
+  static constexpr bool blockable      = false;  ///< writes outputs at the element's input index
   FoundIt found;
   InsertedIt inserted;
 
@@ -266,6 +268,7 @@ struct action_insert_and_find {
 /// insert_or_assign: last writer wins (reference: static_map_ref.inl:486-620).
 struct action_assign {
   static constexpr bool key_then_apply = false;
+  static constexpr bool blockable      = true;
   template <typename Engine, typename Slot>
   __device__ void on_new(Engine const&, index_type, Slot*, Slot const&) const noexcept
   {
@@ -287,6 +290,7 @@ struct action_assign {
 template <typename Op, bool DirectApply>
 struct action_apply {
   static constexpr bool key_then_apply = DirectApply;
+  static constexpr bool blockable      = true;
   Op op;
 
   template <typename Engine, typename Slot>
@@ -306,11 +310,31 @@ struct action_apply {
   }
 };
 
+/// Rare path of the fast mutate kernel (not marked noinline: ptxas 12.9 crashes on that): the
+/// slot is claimable but its image differs from the canonical empty slot (foreign payload bits), so
+/// the general driver - which compares against what it actually observes - finishes the key.
+template <int ChunkSlots, load_policy Policy, typename Engine, typename Input, typename Action>
+__device__ bool mutate_slow_path(
+  Engine& engine, Input const& val, index_type idx, Action& action)
+{
+  using slot_type    = typename Engine::value_type;
+  auto const desired = engine.native_value(val);
+  auto const res     = engine.template insert_driver<ChunkSlots, Policy>(
+    val, [&](slot_type* t, slot_type& e, auto const&) { return engine.try_claim(t, e, desired); });
+  if (res.second) {
+    action.on_new(engine, idx, res.first, desired);
+  } else {
+    action.on_present(engine, idx, res.first, *res.first, desired);
+  }
+  return res.second;
+}
+
 template <int BlockSize,
           int KeysPerThread,
           int ChunkSlots,
           bool CasFirst,
           bool Counted,
+          load_policy Policy,
           typename InputIt,
           typename StencilIt,
           typename Predicate,
@@ -333,7 +357,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
   using input_type = decltype(engine.heterogeneous_value(read_input(first, index_type{0})));
   static_assert(Engine::single_cas, "fast mutate path needs one-shot claimable slots");
   constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
-  constexpr auto policy     = load_policy::coherent;
+  constexpr auto policy     = Policy;
   // claim only the key half, then combine the payload in place (insert_or_apply direct mode)
   constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
 
@@ -409,18 +433,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
               action.on_present(engine, idx, address, seen[j], desired);
               pending &= ~(1u << j);
             } else if (state == equal_result::AVAILABLE) {
-              // still claimable but not bit-identical to the empty image (foreign payload):
-              // leave it to the general driver, which compares against what it observes
-              auto const res = engine.template insert_driver<ChunkSlots, policy>(
-                val[j], [&](slot_type* t, slot_type& e, auto const&) {
-                  return engine.try_claim(t, e, desired);
-                });
-              if (res.second) {
-                action.on_new(engine, idx, res.first, desired);
-                ++mine;
-              } else {
-                action.on_present(engine, idx, res.first, *res.first, desired);
-              }
+              // still claimable but not bit-identical to the empty image (foreign payload)
+              mine += mutate_slow_path<ChunkSlots, policy>(engine, val[j], idx, action);
               pending &= ~(1u << j);
             } else {
               // somebody else's key lives here now: move on, next round loads
@@ -518,6 +532,133 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void generic_mutate_kernel(InputIt firs
     }
   }
 
+  if constexpr (Counted) { accumulate_count(num_new, mine); }
+}
+
+// =================================================================================================
+// L2-blocked mutation, pass 1: route the batch by table region
+// =================================================================================================
+//
+// Measured on B200 (tools/microbench.cu): an L2 miss to a random table sector costs the same
+// whether 16 or 128 bytes are wanted - about 37.9 G misses/s chip-wide, every one fetching a 128-byte
+// line - while sectors that are already in the 126 MB L2 are served at ~280 G/s. A mutation on a
+// table larger than L2 therefore pays one DRAM line fetch per key plus one write-back per new key,
+// and that, not the probing code, bounds cuco-style insertion at ~23 Gops/s.
+//
+// The blocked path spends two streaming passes to get rid of almost all of those misses: pass 1
+// (this kernel) scatters the batch into per-region segments of a scratch buffer, a region being a
+// contiguous slice of the slot array of about 32 MB; pass 2 runs the ordinary mutate kernel over the
+// segments in region order, so at any time the keys in flight target one or two regions that stay
+// resident in L2. Every table line is then fetched from DRAM once per batch instead of once per key.
+//
+// Segments have a fixed capacity (expected load + slack); an element whose segment is full is
+// finished right here through the general driver, which keeps the path correct for arbitrarily
+// skewed inputs without a counting pre-pass.
+
+/// Maps a home slot to its region: floor(slot * num_regions / capacity) by multiply-high.
+struct region_map {
+  std::uint64_t scale;  ///< ceil(2^64 * num_regions / capacity) clamped so the result < num_regions
+  std::uint32_t num_regions;
+
+  __host__ __device__ std::uint32_t operator()(std::uint64_t slot) const noexcept
+  {
+#if defined(__CUDA_ARCH__)
+    auto const r = static_cast<std::uint32_t>(__umul64hi(slot, scale));
+#else
+    auto const r = static_cast<std::uint32_t>((static_cast<unsigned __int128>(slot) * scale) >> 64);
+#endif
+    return r < num_regions ? r : num_regions - 1;
+  }
+};
+
+/// Pass-2 predicate: virtual element i of the segmented scratch buffer exists.
+struct segment_live {
+  unsigned int const* counts;  ///< elements stored per region (may exceed segment_capacity: clamped)
+  std::uint32_t segment_capacity;
+
+  __device__ bool operator()(index_type i) const noexcept
+  {
+    auto const region = static_cast<std::uint32_t>(i / segment_capacity);
+    auto const local  = static_cast<std::uint32_t>(i - index_type{region} * segment_capacity);
+    return local < counts[region];
+  }
+};
+
+constexpr int route_items_per_thread = 8;
+constexpr int route_max_regions      = 2048;
+
+template <int BlockSize,
+          int ChunkSlots,
+          bool Counted,
+          typename InputIt,
+          typename Counter,
+          typename Engine,
+          typename Action>
+CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
+                                                           index_type n,
+                                                           typename Engine::value_type* scratch,
+                                                           unsigned int* region_counts,
+                                                           region_map regions,
+                                                           std::uint32_t segment_capacity,
+                                                           Counter* num_new,
+                                                           Engine engine,
+                                                           Action action)
+{
+  using slot_type = typename Engine::value_type;
+  extern __shared__ unsigned int route_smem[];
+  unsigned int* const tile_hist = route_smem;                         // [num_regions]
+  unsigned int* const tile_base = route_smem + regions.num_regions;   // [num_regions]
+  constexpr index_type tile = index_type{BlockSize} * route_items_per_thread;
+  unsigned long long mine   = 0;
+
+  for (index_type base = index_type{blockIdx.x} * tile; base < n;
+       base += index_type{gridDim.x} * tile) {
+    for (std::uint32_t r = threadIdx.x; r < regions.num_regions; r += BlockSize) {
+      tile_hist[r] = 0;
+    }
+    __syncthreads();
+
+    slot_type image[route_items_per_thread];
+    std::uint32_t region[route_items_per_thread];
+    std::uint32_t rank[route_items_per_thread];
+#pragma unroll
+    for (int j = 0; j < route_items_per_thread; ++j) {
+      index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
+      region[j]            = 0xffffffffu;
+      if (idx < n) {
+        auto const val = engine.heterogeneous_value(read_input(first, idx));
+        image[j]       = engine.native_value(val);
+        region[j]      = regions(engine.make_cursor(Engine::key_of(val)).slot);
+      }
+      // one shared-memory atomic per distinct region per warp
+      unsigned const peers  = __match_any_sync(0xffffffffu, region[j]);
+      int const leader      = __ffs(peers) - 1;
+      unsigned const before = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+      unsigned start        = 0;
+      if (region[j] != 0xffffffffu && leader == static_cast<int>(threadIdx.x & 31)) {
+        start = atomicAdd(&tile_hist[region[j]], __popc(peers));
+      }
+      rank[j] = __shfl_sync(0xffffffffu, start, leader) + before;
+    }
+    __syncthreads();
+    for (std::uint32_t r = threadIdx.x; r < regions.num_regions; r += BlockSize) {
+      tile_base[r] = tile_hist[r] ? atomicAdd(&region_counts[r], tile_hist[r]) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < route_items_per_thread; ++j) {
+      if (region[j] == 0xffffffffu) { continue; }
+      auto const pos = static_cast<std::uint64_t>(tile_base[region[j]]) + rank[j];
+      if (pos < segment_capacity) {
+        scratch[static_cast<std::uint64_t>(region[j]) * segment_capacity + pos] = image[j];
+      } else {
+        // segment full (heavily skewed input): finish this element now, unblocked
+        index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
+        mine += mutate_slow_path<ChunkSlots, load_policy::streaming>(engine, image[j], idx, action);
+      }
+    }
+    __syncthreads();
+  }
   if constexpr (Counted) { accumulate_count(num_new, mine); }
 }
 

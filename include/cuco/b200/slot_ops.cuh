@@ -26,8 +26,10 @@ namespace cuco::b200 {
 /// How a table read interacts with the caches.
 enum class load_policy : int {
   plain,     ///< ordinary generic load (works on shared memory too)
-  readonly,  ///< table is not written during the kernel: non-coherent path, do not allocate in L1
-  coherent   ///< table is being mutated by the same kernel: L2-coherent read, bypass L1
+  readonly,  ///< table is not written during the kernel: non-coherent path, no L1 allocation
+  streaming, ///< weak global load that does not allocate in L1 (mutating kernels: staleness is
+             ///< harmless because every claim is validated by the CAS result)
+  coherent   ///< relaxed.gpu load served by L2 (only needed when a stale value would be acted on)
 };
 
 /// Raw bytes of one probing chunk.
@@ -37,6 +39,31 @@ struct alignas(Bytes < 16 ? Bytes : 16) raw_chunk {
   std::uint32_t w[Bytes / 4];
 };
 
+#define CUCO_B200_LD(PREFIX, BYTES_TAG)                                                          \
+  if constexpr (BYTES_TAG == 4) {                                                                \
+    asm volatile(PREFIX ".u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p) : "memory");                    \
+  } else if constexpr (BYTES_TAG == 8) {                                                         \
+    asm volatile(PREFIX ".v2.u32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p) : "memory"); \
+  } else if constexpr (BYTES_TAG == 16) {                                                        \
+    asm volatile(PREFIX ".v4.u32 {%0,%1,%2,%3}, [%4];"                                           \
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])                        \
+                 : "l"(p)                                                                        \
+                 : "memory");                                                                    \
+  } else {                                                                                       \
+    asm volatile(PREFIX ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                               \
+                 : "=r"(r.w[0]),                                                                 \
+                   "=r"(r.w[1]),                                                                 \
+                   "=r"(r.w[2]),                                                                 \
+                   "=r"(r.w[3]),                                                                 \
+                   "=r"(r.w[4]),                                                                 \
+                   "=r"(r.w[5]),                                                                 \
+                   "=r"(r.w[6]),                                                                 \
+                   "=r"(r.w[7])                                                                  \
+                 : "l"(p)                                                                        \
+                 : "memory");                                                                    \
+  }
+
+/// Loads `Bytes` (4/8/16/32, naturally aligned) as one instruction: LDG.E.{32,64,128,256}.
 template <int Bytes, load_policy Policy>
 __device__ __forceinline__ raw_chunk<Bytes> load_chunk_bytes(void const* p) noexcept
 {
@@ -48,81 +75,27 @@ __device__ __forceinline__ raw_chunk<Bytes> load_chunk_bytes(void const* p) noex
       auto const v = *static_cast<uint2 const*>(p);
       r.w[0]       = v.x;
       r.w[1]       = v.y;
-    } else if constexpr (Bytes == 16) {
-      auto const v = *static_cast<uint4 const*>(p);
-      r.w[0]       = v.x;
-      r.w[1]       = v.y;
-      r.w[2]       = v.z;
-      r.w[3]       = v.w;
     } else {
       auto const* q = static_cast<uint4 const*>(p);
-      auto const a  = q[0];
-      auto const b  = q[1];
-      r.w[0]        = a.x;
-      r.w[1]        = a.y;
-      r.w[2]        = a.z;
-      r.w[3]        = a.w;
-      r.w[4]        = b.x;
-      r.w[5]        = b.y;
-      r.w[6]        = b.z;
-      r.w[7]        = b.w;
+#pragma unroll
+      for (int i = 0; i < Bytes / 16; ++i) {
+        auto const v   = q[i];
+        r.w[4 * i]     = v.x;
+        r.w[4 * i + 1] = v.y;
+        r.w[4 * i + 2] = v.z;
+        r.w[4 * i + 3] = v.w;
+      }
     }
   } else if constexpr (Policy == load_policy::readonly) {
-    if constexpr (Bytes == 4) {
-      asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
-    } else if constexpr (Bytes == 8) {
-      asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                   : "=r"(r.w[0]), "=r"(r.w[1])
-                   : "l"(p));
-    } else if constexpr (Bytes == 16) {
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
-                   : "l"(p));
-    } else {
-      asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(r.w[0]),
-                     "=r"(r.w[1]),
-                     "=r"(r.w[2]),
-                     "=r"(r.w[3]),
-                     "=r"(r.w[4]),
-                     "=r"(r.w[5]),
-                     "=r"(r.w[6]),
-                     "=r"(r.w[7])
-                   : "l"(p));
-    }
+    CUCO_B200_LD("ld.global.nc.L1::no_allocate", Bytes)
+  } else if constexpr (Policy == load_policy::streaming) {
+    CUCO_B200_LD("ld.global.L1::no_allocate", Bytes)
   } else {
-    if constexpr (Bytes == 4) {
-      asm volatile("ld.relaxed.gpu.global.L1::no_allocate.u32 %0, [%1];"
-                   : "=r"(r.w[0])
-                   : "l"(p)
-                   : "memory");
-    } else if constexpr (Bytes == 8) {
-      asm volatile("ld.relaxed.gpu.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                   : "=r"(r.w[0]), "=r"(r.w[1])
-                   : "l"(p)
-                   : "memory");
-    } else if constexpr (Bytes == 16) {
-      asm volatile("ld.relaxed.gpu.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
-                   : "l"(p)
-                   : "memory");
-    } else {
-      asm volatile(
-        "ld.relaxed.gpu.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(r.w[0]),
-          "=r"(r.w[1]),
-          "=r"(r.w[2]),
-          "=r"(r.w[3]),
-          "=r"(r.w[4]),
-          "=r"(r.w[5]),
-          "=r"(r.w[6]),
-          "=r"(r.w[7])
-        : "l"(p)
-        : "memory");
-    }
+    CUCO_B200_LD("ld.relaxed.gpu.global.L1::no_allocate", Bytes)
   }
   return r;
 }
+#undef CUCO_B200_LD
 
 /// Extracts slot `i` of a chunk as a typed value (folds to register moves).
 template <typename Slot, int Bytes>

@@ -151,8 +151,17 @@ int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream);
 
 /* Launch tuning of the native build (no-op returning 1 in the reference build).
  * keys_per_thread in {1,2,4}; the others are booleans; waves >= 1. Negative = leave unchanged. */
-int cuco_b200_set_tuning(
-  int keys_per_thread, int cas_first, int sector_chunks, int waves, int force_generic, int l2_window);
+int cuco_b200_set_tuning(int keys_per_thread,
+                         int cas_first,
+                         int sector_chunks,
+                         int waves,
+                         int force_generic,
+                         int l2_window,
+                         int coherent_loads);
+
+/* L2-blocked mutation control of the native build: mode -1 auto (tables much larger than L2),
+ * 0 off, 1 always; region_mib = size of the table slice kept L2-resident (<= 0: unchanged). */
+int cuco_b200_set_blocking(int mode, int region_mib);
 
 /* ---- hash-partitioned multi-GPU support (no reference counterpart) --------------
  * owner(key) = mulhi64(murmur_fmix64(key ^ salt), num_parts): high bits of a mix that is independent

@@ -20,8 +20,8 @@ MAP_KINDS = [_cabi.MAP_I64_LP1, _cabi.MAP_I64_DH8, _cabi.MAP_I32_LP4, _cabi.MAP_
              _cabi.MAP_I64_LP1_W2, _cabi.MAP_I32_DH2_W2_MM, _cabi.MAP_I32I64_LP1,
              _cabi.MAP_I64_DH8_X64]
 SET_KINDS = [_cabi.SET_I32_DH4, _cabi.SET_I64_DH4]
-TUNINGS = [  # (keys_per_thread, cas_first, sector_chunks, force_generic)
-    (2, 1, 1, 0), (1, 0, 0, 0), (4, 1, 1, 0), (4, 0, 1, 0), (2, 1, 1, 1)]
+TUNINGS = [  # (keys_per_thread, cas_first, sector_chunks, force_generic, coherent_loads)
+    (2, 0, 1, 0, 0), (1, 0, 0, 0, 1), (4, 1, 1, 0, 0), (4, 0, 1, 0, 1), (2, 1, 1, 1, 0), (1, 1, 1, 0, 0)]
 
 
 def make(kind, lib, **kw):
@@ -47,13 +47,13 @@ def keyset(kind, n, seed, hi=None):
 @pytest.fixture(autouse=True)
 def reset_tuning(native_lib):
     yield
-    native_lib.set_tuning(2, 1, 1, 1, 0, 1)
+    native_lib.set_tuning(2, 0, 1, 1, 0, 1, 0)
 
 
 @pytest.mark.parametrize("tuning", TUNINGS)
 @pytest.mark.parametrize("kind", MAP_KINDS)
 def test_map_insert_find_contains_match_oracle(kind, tuning, native_lib):
-    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1)
+    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1, tuning[4])
     k = cb.KINDS[kind]
     n = 20_000
     keys = keyset(kind, n, 1, hi=n)          # duplicates: ~63 % distinct
@@ -77,7 +77,7 @@ def test_map_insert_find_contains_match_oracle(kind, tuning, native_lib):
 @pytest.mark.parametrize("tuning", TUNINGS[:3])
 @pytest.mark.parametrize("kind", SET_KINDS)
 def test_set_insert_find_contains_match_oracle(kind, tuning, native_lib):
-    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1)
+    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1, tuning[4])
     k = cb.KINDS[kind]
     n = 30_000
     keys = keyset(kind, n, 3, hi=n)
@@ -289,3 +289,40 @@ def test_full_size_round_trip_properties(native_lib):
         t.close()
         del t
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind", [_cabi.MAP_I64_LP1, _cabi.MAP_I64_DH8, _cabi.MAP_I32_LP4, _cabi.SET_I32_DH4])
+def test_l2_blocked_mutations_match_oracle(kind, native_lib):
+    """The routed (L2-blocked) insert / insert_or_assign / insert_or_apply path, forced on for small
+    inputs, including a fully skewed batch that overflows a region segment."""
+    k = cb.KINDS[kind]
+    is_map = k.value is not None
+    n = 60_000
+    try:
+        native_lib.set_blocking(1, 1)  # always, 1 MiB regions
+        streams = {
+            "uniform": keyset(kind, n, 21, hi=n),
+            "skewed": np.concatenate([np.full(n - 100, 7, dtype=np.int64), np.arange(100, dtype=np.int64) + 100]),
+            "unique": np.random.default_rng(5).permutation(4 * n)[:n].astype(np.int64),
+        }
+        for name, keys in streams.items():
+            vals = (keys * 3 + 2) % 1_000_000
+            t = make(kind, native_lib, n=n, load_factor=0.5)
+            ref = oracle.Table.for_kind(kind, n, 0.5)
+            dk = dev(keys, k.key)
+            dv = dev(vals, k.value) if is_map else None
+            assert t.insert(dk, dv) == ref.insert(keys, vals if is_map else None), name
+            assert t.size() == ref.size(), name
+            q = np.concatenate([keys[::3], keyset(kind, 1000, 22, hi=8 * n)])
+            assert np.array_equal(t.find(dev(q, k.key)).cpu().numpy(), ref.find(q)), name
+            if is_map:
+                t.insert_or_assign(dk, dev(vals + 9, k.value)); ref.insert_or_assign(keys, vals + 9)
+                assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
+                t.clear(); ref.clear()
+                ones = np.ones(n, dtype=np.int64)
+                t.insert_or_apply(dk, dev(ones, k.value), op="plus"); ref.insert_or_apply(keys, ones, oracle.PLUS)
+                assert t.size() == ref.size()
+                assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
+            t.close()
+    finally:
+        native_lib.set_blocking(-1, 32)

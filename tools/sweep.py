@@ -66,18 +66,31 @@ if ref is not None:
     point(ref, "cuco", "linear_probing", 1, 0.5, upairs, ukeys, "unique")
     point(ref, "cuco", "linear_probing", 1, 0.8, upairs, ukeys, "unique")
 
-for kpt, cas_first, sector, waves in itertools.product((1, 2, 4), (0, 1), (0, 1), (1, 2)):
-    native.set_tuning(kpt, cas_first, sector, waves, 0, 1)
-    label = f"ours kpt={kpt} cas_first={cas_first} sector={sector} waves={waves}"
-    for probing, cg, lf in configs[:1] + configs[2:3]:
-        point(native, label, probing, cg, lf, pairs, keys, "uniform")
-# best-guess config across all points incl. unique keys (true fill = LF)
-for kpt, cas_first in ((2, 1), (4, 1), (4, 0), (2, 0)):
-    native.set_tuning(kpt, cas_first, 1, 1, 0, 1)
-    label = f"ours kpt={kpt} cas_first={cas_first} sector=1 waves=1"
+def tune(kpt=2, cas_first=0, sector=1, waves=1, generic=0, coherent=0, blocked=0, region=32):
+    native.set_tuning(kpt, cas_first, sector, waves, generic, 1, coherent)
+    native.set_blocking(blocked, region)
+    return f"ours kpt={kpt} casf={cas_first} sec={sector} waves={waves} gen={generic} coh={coherent} blk={blocked} reg={region}"
+
+
+lp, dh = configs[0], configs[2]
+# 1. unblocked insert: load policy, cas-first, keys per thread, waves
+for kpt, cas_first, coherent, waves in itertools.product((1, 2, 4), (0, 1), (0, 1), (1, 4)):
+    label = tune(kpt=kpt, cas_first=cas_first, coherent=coherent, waves=waves)
+    point(native, label, *lp, pairs, keys, "uniform")
+# 2. lookups: waves and kpt
+for kpt, waves in itertools.product((1, 2, 4), (1, 2, 4, 8, 64)):
+    label = tune(kpt=kpt, waves=waves)
+    point(native, label, *lp, pairs, keys, "uniform")
+# 3. blocked insert: region size and kpt
+for kpt, region in itertools.product((1, 2, 4), (8, 16, 32, 48, 64)):
+    label = tune(kpt=kpt, blocked=1, region=region)
+    point(native, label, *lp, pairs, keys, "uniform")
+# 4. full table of the C2 points with the blocked path on/off
+for blocked in (0, 1):
+    label = tune(blocked=blocked)
     for probing, cg, lf in configs:
         point(native, label, probing, cg, lf, pairs, keys, "uniform")
     point(native, label, "linear_probing", 1, 0.5, upairs, ukeys, "unique")
     point(native, label, "linear_probing", 1, 0.8, upairs, ukeys, "unique")
-native.set_tuning(2, 1, 1, 1, 1, 1)
-point(native, "ours generic", "linear_probing", 1, 0.5, pairs, keys, "uniform")
+label = tune(generic=1)
+point(native, label, *lp, pairs, keys, "uniform")
