@@ -429,12 +429,17 @@ int cuco_b200_set_tuning(int keys_per_thread,
   return 1;
 #else
   auto& t = cuco::b200::tuning();
-  if (keys_per_thread == 1 || keys_per_thread == 2 || keys_per_thread == 4) {
-    t.keys_per_thread = keys_per_thread;
+  // keys_per_thread = lookups + 10 * mutations when >= 10 (e.g. 12 = lookups 2, mutations 1)
+  int const lookup_kpt = keys_per_thread % 10, mutate_kpt = keys_per_thread / 10;
+  if (lookup_kpt == 1 || lookup_kpt == 2 || lookup_kpt == 4) { t.keys_per_thread = lookup_kpt; }
+  if (mutate_kpt == 1 || mutate_kpt == 2 || mutate_kpt == 4) {
+    t.mutate_keys_per_thread = mutate_kpt;
+  } else if (keys_per_thread > 0 && keys_per_thread < 10) {
+    t.mutate_keys_per_thread = lookup_kpt;  // single digit sets both
   }
   if (cas_first >= 0) { t.cas_first = cas_first != 0; }
   if (sector_chunks >= 0) { t.sector_chunks = sector_chunks != 0; }
-  if (waves >= 1) { t.waves = waves; }
+  if (waves >= 0) { t.waves = waves; }
   if (force_generic >= 0) { t.force_generic = force_generic != 0; }
   if (l2_window >= 0) { t.l2_window = l2_window != 0; }
   if (coherent_loads >= 0) { t.coherent_loads = coherent_loads != 0; }

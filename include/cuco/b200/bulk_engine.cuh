@@ -48,7 +48,11 @@ struct tuning_t {
   bool cas_first       = false; ///< inserts start with the CAS instead of a load (pays off only
                                 ///< when nearly every key is new: a failed CAS still dirties the sector)
   bool sector_chunks   = true;  ///< 32-byte chunk loads (else one window per load)
-  int waves            = 1;     ///< grid = waves * resident CTAs (persistent, grid-stride)
+  int waves            = 0;     ///< 0: one CTA per tile; k > 0: persistent grid of k * resident CTAs.
+                                ///< Measured on B200: one tile per CTA is 10-30 % faster than a
+                                ///< one-wave persistent grid on every op (profiles/r01_sweep.md)
+  int mutate_keys_per_thread = 1;  ///< insert-type kernels: 2 dependent memory operations per key,
+                                   ///< so occupancy (fewer registers) beats per-thread MLP
   bool force_generic   = false; ///< route everything through the one-key-per-thread fallback
   bool l2_window       = true;  ///< persisting-L2 access window for tables <= l2_window_bytes
   bool coherent_loads  = false; ///< mutating kernels read the table with relaxed.gpu loads
@@ -65,7 +69,8 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_KPT")) { t.keys_per_thread = std::atoi(s); }
   if (char const* s = std::getenv("CUCO_B200_CAS_FIRST")) { t.cas_first = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_SECTOR")) { t.sector_chunks = std::atoi(s) != 0; }
-  if (char const* s = std::getenv("CUCO_B200_WAVES")) { t.waves = std::max(1, std::atoi(s)); }
+  if (char const* s = std::getenv("CUCO_B200_WAVES")) { t.waves = std::max(0, std::atoi(s)); }
+  if (char const* s = std::getenv("CUCO_B200_MUTATE_KPT")) { t.mutate_keys_per_thread = std::atoi(s); }
   if (char const* s = std::getenv("CUCO_B200_GENERIC")) { t.force_generic = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_L2_WINDOW")) { t.l2_window = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_COHERENT")) { t.coherent_loads = std::atoi(s) != 0; }
@@ -98,7 +103,9 @@ inline unsigned persistent_grid(Kernel kernel, int block_size, cuco::detail::ind
 {
   static int resident = 0;  // one per kernel instantiation; devices in a process are identical
   if (resident == 0) { resident = cuco::detail::max_occupancy_grid_size(block_size, kernel); }
-  auto const want = static_cast<cuco::detail::index_type>(resident) * tuning().waves;
+  auto const waves = tuning().waves;
+  auto const want  = waves > 0 ? static_cast<cuco::detail::index_type>(resident) * waves
+                               : cuco::detail::index_type{0x7fffffff};
   return static_cast<unsigned>(std::max<cuco::detail::index_type>(1, std::min(tiles, want)));
 }
 
@@ -700,7 +707,7 @@ class table_engine {
           go(std::false_type{}, std::false_type{});
 #endif
         };
-        dispatch_variant<engine_t>(run);
+        dispatch_variant<engine_t, true>(run);
         return;
       }
     }
@@ -801,12 +808,12 @@ class table_engine {
         kernel<<<persistent_grid(kernel, block_size, tiles), block_size, 0, stream.get()>>>(
           first, virtual_n, stencil, live, counter, engine, action);
       };
-      dispatch_variant<EngineT>(run);
+      dispatch_variant<EngineT, true>(run);
     }
   }
 
   /// Picks the (keys per thread, chunk width) instantiation.
-  template <typename EngineT, typename Run>
+  template <typename EngineT, bool Mutating = false, typename Run>
   static void dispatch_variant(Run&& run)
   {
     constexpr int sector = EngineT::sector_chunk_slots;
@@ -820,13 +827,13 @@ class table_engine {
         run(kpt, std::integral_constant<int, window>{});
       }
     };
-    switch (t.keys_per_thread) {
+    switch (Mutating ? t.mutate_keys_per_thread : t.keys_per_thread) {
       case 1: with_chunk(std::integral_constant<int, 1>{}); break;
       case 4: with_chunk(std::integral_constant<int, 4>{}); break;
       default: with_chunk(std::integral_constant<int, 2>{}); break;
     }
 #else
-    run(std::integral_constant<int, 2>{}, std::integral_constant<int, sector>{});
+    run(std::integral_constant<int, Mutating ? 1 : 2>{}, std::integral_constant<int, sector>{});
 #endif
   }
 

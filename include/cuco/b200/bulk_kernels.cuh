@@ -51,6 +51,14 @@ __device__ __forceinline__ auto read_input(It first, index_type i)
   }
 }
 
+/// Register storage for a value of a type that may lack a default constructor (probe keys and
+/// input elements are user types; they only need to be trivially copyable, like kernel arguments).
+template <typename T>
+union uninitialized {
+  T value;
+  __device__ uninitialized() {}
+};
+
 /// Adds a per-thread count into a global counter: warp shuffle reduce, one atomic per warp.
 template <typename Counter>
 __device__ __forceinline__ void accumulate_count(Counter* counter, unsigned long long mine)
@@ -120,7 +128,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void lookup_kernel(InputIt first,
 
   for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
        tile_base += index_type{gridDim.x} * tile) {
-    probe_type key[KeysPerThread];
+    uninitialized<probe_type> key[KeysPerThread];
     cursor cur[KeysPerThread];
     unsigned pending = 0;
 
@@ -129,8 +137,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void lookup_kernel(InputIt first,
       index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
       if (idx < n) {
         if (pred(*(stencil + idx))) {
-          key[j] = read_input(first, idx);
-          cur[j] = engine.make_cursor(key[j]);
+          key[j].value = read_input(first, idx);
+          cur[j]       = engine.make_cursor(key[j].value);
           pending |= 1u << j;
         } else {
           *(out + idx) = emit.miss();
@@ -156,7 +164,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void lookup_kernel(InputIt first,
           for (int i = 0; i < ChunkSlots; ++i) {
             if (!done && i >= begin_off && i < begin_off + valid) {
               auto const slot  = chunk_slot<slot_type>(raw[j], i);
-              auto const state = engine.classify_lookup(key[j], Engine::key_of(slot));
+              auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
               if (state == equal_result::EQUAL) {
                 *(out + idx) = emit.hit(slot);
                 done         = true;
@@ -367,7 +375,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
 
   for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
        tile_base += index_type{gridDim.x} * tile) {
-    input_type val[KeysPerThread];
+    uninitialized<input_type> val[KeysPerThread];
     cursor cur[KeysPerThread];
     unsigned pending = 0;  // bit j: key j still in flight
     unsigned claim   = 0;  // bit j: next action of key j is a CAS at cur[j].slot (else a chunk load)
@@ -376,8 +384,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
     for (int j = 0; j < KeysPerThread; ++j) {
       index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
       if (idx < n && pred(*(stencil + idx))) {
-        val[j] = engine.heterogeneous_value(read_input(first, idx));
-        cur[j] = engine.make_cursor(Engine::key_of(val[j]));
+        val[j].value = engine.heterogeneous_value(read_input(first, idx));
+        cur[j]       = engine.make_cursor(Engine::key_of(val[j].value));
         pending |= 1u << j;
         if constexpr (CasFirst) { claim |= 1u << j; }
       }
@@ -396,13 +404,13 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
               key_type expected_key = Engine::key_of(empty_slot);
               cuda::atomic_ref<key_type, Engine::thread_scope> key_ref{(table + cur[j].slot)->first};
               key_ref.compare_exchange_strong(expected_key,
-                                              static_cast<key_type>(Engine::key_of(val[j])),
+                                              static_cast<key_type>(Engine::key_of(val[j].value)),
                                               cuda::memory_order_relaxed);
               seen[j]       = empty_slot;
               seen[j].first = expected_key;
             } else {
               seen[j] = cas_slot<Engine::thread_scope>(
-                table + cur[j].slot, empty_slot, engine.native_value(val[j]));
+                table + cur[j].slot, empty_slot, engine.native_value(val[j].value));
             }
           } else {
             raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]);
@@ -415,8 +423,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
       for (int j = 0; j < KeysPerThread; ++j) {
         if (!(pending & (1u << j))) { continue; }
         index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
-        auto const& key      = Engine::key_of(val[j]);
-        auto const desired   = engine.native_value(val[j]);
+        auto const& key      = Engine::key_of(val[j].value);
+        auto const desired   = engine.native_value(val[j].value);
 
         if (claim & (1u << j)) {
           auto* const address = table + cur[j].slot;
@@ -434,7 +442,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
               pending &= ~(1u << j);
             } else if (state == equal_result::AVAILABLE) {
               // still claimable but not bit-identical to the empty image (foreign payload)
-              mine += mutate_slow_path<ChunkSlots, policy>(engine, val[j], idx, action);
+              mine += mutate_slow_path<ChunkSlots, policy>(engine, val[j].value, idx, action);
               pending &= ~(1u << j);
             } else {
               // somebody else's key lives here now: move on, next round loads

@@ -26,7 +26,9 @@ namespace cuco::b200 {
   static_assert(Ref::cg_size == 1, \
                 "Non-CG operation is incompatible with the current probing scheme")
 
-template <typename Ref>
+/// `Tag` only makes the base unique per mixin: a ref inherits several mixins, and a shared base type
+/// would make the downcast to `Ref` ambiguous.
+template <typename Ref, typename Tag>
 struct mixin_base {
  protected:
   __device__ auto& self() noexcept { return static_cast<Ref&>(*this); }
@@ -35,7 +37,7 @@ struct mixin_base {
 
 // ---- insert --------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_insert : mixin_base<Ref> {
+struct mixin_insert : mixin_base<Ref, op::insert_tag> {
   /// Inserts `value`; true iff the key was not present before.
   template <typename Value>
   __device__ bool insert(Value const& value) noexcept
@@ -54,7 +56,7 @@ struct mixin_insert : mixin_base<Ref> {
 
 // ---- insert_and_find -----------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_insert_and_find : mixin_base<Ref> {
+struct mixin_insert_and_find : mixin_base<Ref, op::insert_and_find_tag> {
   /// Inserts `value` if absent; returns {handle to the resident slot, whether this call created it}.
   /// The handle's payload is always a published value, never the empty sentinel.
   template <typename Value>
@@ -74,7 +76,7 @@ struct mixin_insert_and_find : mixin_base<Ref> {
 
 // ---- erase ---------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_erase : mixin_base<Ref> {
+struct mixin_erase : mixin_base<Ref, op::erase_tag> {
   /// Replaces the entry of `key` by a tombstone; true iff this call removed it.
   template <typename ProbeKey>
   __device__ bool erase(ProbeKey const& key) noexcept
@@ -93,7 +95,7 @@ struct mixin_erase : mixin_base<Ref> {
 
 // ---- contains ------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_contains : mixin_base<Ref> {
+struct mixin_contains : mixin_base<Ref, op::contains_tag> {
   template <typename ProbeKey>
   [[nodiscard]] __device__ bool contains(ProbeKey const& key) const noexcept
   {
@@ -111,7 +113,7 @@ struct mixin_contains : mixin_base<Ref> {
 
 // ---- count ---------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_count : mixin_base<Ref> {
+struct mixin_count : mixin_base<Ref, op::count_tag> {
   template <typename ProbeKey>
   [[nodiscard]] __device__ auto count(ProbeKey const& key) const noexcept
   {
@@ -129,7 +131,7 @@ struct mixin_count : mixin_base<Ref> {
 
 // ---- find ----------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_find : mixin_base<Ref> {
+struct mixin_find : mixin_base<Ref, op::find_tag> {
   /// Handle to the slot holding `key`, or `end()`.
   template <typename ProbeKey>
   [[nodiscard]] __device__ auto find(ProbeKey const& key) const noexcept
@@ -148,7 +150,7 @@ struct mixin_find : mixin_base<Ref> {
 
 // ---- for_each ------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_for_each : mixin_base<Ref> {
+struct mixin_for_each : mixin_base<Ref, op::for_each_tag> {
   /// Invokes `callback(slot_handle)` for every entry whose key equals `key`.
   template <typename ProbeKey, typename Callback>
   __device__ void for_each(ProbeKey const& key, Callback&& callback) const noexcept
@@ -170,7 +172,7 @@ struct mixin_for_each : mixin_base<Ref> {
 
 // ---- insert_or_assign (maps) ---------------------------------------------------------------------
 template <typename Ref, int CGSize>
-struct mixin_insert_or_assign : mixin_base<Ref> {
+struct mixin_insert_or_assign : mixin_base<Ref, op::insert_or_assign_tag> {
   /// Upsert: afterwards the key maps to `value.second` (last writer wins among concurrent calls).
   template <typename Value>
   __device__ void insert_or_assign(Value const& value) noexcept
@@ -212,7 +214,7 @@ struct mixin_insert_or_assign : mixin_base<Ref> {
 
 // ---- insert_or_apply (maps) ----------------------------------------------------------------------
 template <typename Ref, typename Mapped, int CGSize>
-struct mixin_insert_or_apply : mixin_base<Ref> {
+struct mixin_insert_or_apply : mixin_base<Ref, op::insert_or_apply_tag> {
   /// Aggregating upsert: the first arrival stores its payload, every other arrival runs
   /// `op(cuda::atomic_ref<Mapped, Scope>{slot.second}, value.second)`. True iff newly inserted.
   template <typename Value, typename Op>

@@ -150,7 +150,9 @@ int cuco_b200_retrieve_all(
 int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream);
 
 /* Launch tuning of the native build (no-op returning 1 in the reference build).
- * keys_per_thread in {1,2,4}; the others are booleans; waves >= 1. Negative = leave unchanged. */
+ * keys_per_thread in {1,2,4} sets lookups and mutations alike, or L + 10*M sets them separately
+ * (12 = lookups 2, mutations 1); waves = 0 launches one CTA per tile, k > 0 a persistent grid of
+ * k waves; the others are booleans. Negative = leave unchanged. */
 int cuco_b200_set_tuning(int keys_per_thread,
                          int cas_first,
                          int sector_chunks,

@@ -34,7 +34,7 @@ def test_argument_errors_do_not_need_a_gpu(native_lib):
     assert rc == 3  # erased-key constructor takes a capacity
     rc = native_lib.insert(None, None, None, 10, None, None)
     assert rc == 3
-    assert native_lib.set_tuning(2, 0, 1, 1, 0, 1, 0) == 0
+    assert native_lib.set_tuning(12, 0, 1, 0, 0, 1, 0) == 0
     assert native_lib.capacity(None) == -1
 
 

@@ -20,8 +20,9 @@ MAP_KINDS = [_cabi.MAP_I64_LP1, _cabi.MAP_I64_DH8, _cabi.MAP_I32_LP4, _cabi.MAP_
              _cabi.MAP_I64_LP1_W2, _cabi.MAP_I32_DH2_W2_MM, _cabi.MAP_I32I64_LP1,
              _cabi.MAP_I64_DH8_X64]
 SET_KINDS = [_cabi.SET_I32_DH4, _cabi.SET_I64_DH4]
-TUNINGS = [  # (keys_per_thread, cas_first, sector_chunks, force_generic, coherent_loads)
-    (2, 0, 1, 0, 0), (1, 0, 0, 0, 1), (4, 1, 1, 0, 0), (4, 0, 1, 0, 1), (2, 1, 1, 1, 0), (1, 1, 1, 0, 0)]
+TUNINGS = [  # (keys_per_thread, cas_first, sector_chunks, force_generic, coherent_loads, waves)
+    (12, 0, 1, 0, 0, 0), (1, 0, 0, 0, 1, 1), (4, 1, 1, 0, 0, 2), (4, 0, 1, 0, 1, 0), (2, 1, 1, 1, 0, 0),
+    (1, 1, 1, 0, 0, 1), (2, 0, 1, 0, 0, 1)]
 
 
 def make(kind, lib, **kw):
@@ -47,13 +48,13 @@ def keyset(kind, n, seed, hi=None):
 @pytest.fixture(autouse=True)
 def reset_tuning(native_lib):
     yield
-    native_lib.set_tuning(2, 0, 1, 1, 0, 1, 0)
+    native_lib.set_tuning(12, 0, 1, 0, 0, 1, 0)
 
 
 @pytest.mark.parametrize("tuning", TUNINGS)
 @pytest.mark.parametrize("kind", MAP_KINDS)
 def test_map_insert_find_contains_match_oracle(kind, tuning, native_lib):
-    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1, tuning[4])
+    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], tuning[5], tuning[3], 1, tuning[4])
     k = cb.KINDS[kind]
     n = 20_000
     keys = keyset(kind, n, 1, hi=n)          # duplicates: ~63 % distinct
@@ -77,7 +78,7 @@ def test_map_insert_find_contains_match_oracle(kind, tuning, native_lib):
 @pytest.mark.parametrize("tuning", TUNINGS[:3])
 @pytest.mark.parametrize("kind", SET_KINDS)
 def test_set_insert_find_contains_match_oracle(kind, tuning, native_lib):
-    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], 1, tuning[3], 1, tuning[4])
+    native_lib.set_tuning(tuning[0], tuning[1], tuning[2], tuning[5], tuning[3], 1, tuning[4])
     k = cb.KINDS[kind]
     n = 30_000
     keys = keyset(kind, n, 3, hi=n)
