@@ -55,8 +55,13 @@ _PROTOTYPES = {
     "cuco_b200_erase": (_int, [_vp, _vp, _i64, _vp]),
     "cuco_b200_retrieve_all": (_int, [_vp, _vp, _vp, _pi64, _vp]),
     "cuco_b200_rehash": (_int, [_vp, _i64, _vp]),
+    "cuco_b200_insert_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "cuco_b200_find_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "cuco_b200_contains_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "cuco_b200_insert_and_find_host": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cuco_b200_set_tuning": (_int, [_int, _int, _int, _int, _int, _int, _int]),
     "cuco_b200_set_blocking": (_int, [_int, _int]),
+    "cuco_b200_set_blocking_variant": (_int, [_int, _int, _int]),
     "cuco_b200_partition_count": (_int, [_vp, _int, _int, _i64, _int, _u64, _vp, _vp]),
     "cuco_b200_partition_scatter": (
         _int, [_vp, _vp, _int, _int, _int, _i64, _int, _u64, _vp, _vp, _vp, _vp, _vp]),

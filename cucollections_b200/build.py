@@ -71,17 +71,22 @@ def _compile(job):
 def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], reference: bool, verbose: bool):
     build_dir.mkdir(parents=True, exist_ok=True)
     lib.parent.mkdir(parents=True, exist_ok=True)
-    dep_hash = _tree_hash([CSRC, include / "cuco", ROOT / "include" / "cuco_b200.h"])
+    # each object depends on its own source, the shared shim header and the header tree it
+    # instantiates; cabi_core.cu additionally on the C header it implements
+    headers = _tree_hash([include / "cuco", CSRC / "cabi_table.hpp"])
+    core_hash = headers + _tree_hash([CSRC / "cabi_core.cu", ROOT / "include" / "cuco_b200.h",
+                                      ROOT / "include" / "cuco" / "b200"])
+    kind_hash = headers + _tree_hash([CSRC / "cabi_kind.cu"])
     jobs = []
     base = [f"-I{include}", *extra]
-    jobs.append((CSRC / "cabi_core.cu", build_dir / "cabi_core.o", base, ""))
+    jobs.append((CSRC / "cabi_core.cu", build_dir / "cabi_core.o", base, core_hash))
     for k in range(NUM_KINDS):
         flags = [*base, f"-DCUCO_SHIM_KIND={k}"]
         if not reference and k in TUNABLE_KINDS:
             flags.append("-DCUCO_B200_TUNABLE=1")
-        jobs.append((CSRC / "cabi_kind.cu", build_dir / f"cabi_kind_{k}.o", flags, ""))
-    jobs = [(s, o, f, hashlib.sha256((dep_hash + " ".join(map(str, f)) + " ".join(COMMON)).encode()).hexdigest())
-            for (s, o, f, _) in jobs]
+        jobs.append((CSRC / "cabi_kind.cu", build_dir / f"cabi_kind_{k}.o", flags, kind_hash))
+    jobs = [(s, o, f, hashlib.sha256((h + " ".join(map(str, f)) + " ".join(COMMON)).encode()).hexdigest())
+            for (s, o, f, h) in jobs]
     workers = max(1, min(len(jobs), (os.cpu_count() or 4)))
     objs = []
     with cf.ThreadPoolExecutor(workers) as pool:

@@ -200,6 +200,43 @@ class _Table:
 
     insert_and_find_async = insert_and_find
 
+    # -- host-buffer variants (cuco_b200_*_host): chunked, copies overlapped with the kernels --------
+    def _host_keys(self, keys: torch.Tensor, what="keys") -> torch.Tensor:
+        if keys.device.type != "cpu":
+            raise ValueError(f"{what} must be a CPU tensor (pinned for full PCIe speed)")
+        if keys.dtype != self.kind.key:
+            raise TypeError(f"{what} must be {self.kind.key}, got {keys.dtype}")
+        return keys.contiguous()
+
+    def insert_host(self, keys, values=None) -> None:
+        """insert_async of a batch living in host memory. Stream-ordered."""
+        if self.kind.value is not None and values is None:
+            if keys.dim() != 2 or keys.shape[1] != 2 or self.kind.key != self.kind.value:
+                raise ValueError("pass an [n, 2] pair tensor (same key/payload dtype) or keys and values")
+            k, v, n = self._host_keys(keys, "pairs"), None, keys.shape[0]
+        else:
+            k = self._host_keys(keys)
+            v, n = (None if values is None else values.contiguous()), k.numel()
+            if v is not None and (v.dtype != self.kind.value or v.device.type != "cpu" or v.numel() != n):
+                raise TypeError(f"values must be a CPU tensor of {self.kind.value} with one entry per key")
+        self._call(self._lib.insert_host, _ptr(k), _ptr(v), n, self._stream())
+
+    def find_host(self, keys, out=None) -> torch.Tensor:
+        """find_async from host keys into a host output tensor. Stream-ordered: synchronise the
+        current stream before reading `out`."""
+        k = self._host_keys(keys)
+        if out is None:
+            out = torch.empty(k.numel(), dtype=self._payload_dtype(), pin_memory=True)
+        self._call(self._lib.find_host, _ptr(k), _ptr(out), k.numel(), self._stream())
+        return out
+
+    def contains_host(self, keys, out=None) -> torch.Tensor:
+        k = self._host_keys(keys)
+        if out is None:
+            out = torch.empty(k.numel(), dtype=torch.bool, pin_memory=True)
+        self._call(self._lib.contains_host, _ptr(k), _ptr(out), k.numel(), self._stream())
+        return out
+
     def erase(self, keys) -> None:
         k = self._check_keys(keys)
         self._call(self._lib.erase, _ptr(k), k.numel(), self._stream())

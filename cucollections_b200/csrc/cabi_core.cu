@@ -17,6 +17,11 @@
 #include <exception>
 #include <new>
 #include <stdexcept>
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 
 namespace {
@@ -224,6 +229,185 @@ unsigned route_grid(std::int64_t n, std::int64_t per_block)
   return static_cast<unsigned>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
+
+// ================================================================================================
+// host-buffer pipeline: H2D of chunk i+1, table kernels on chunk i and D2H of chunk i-1 overlap
+// ================================================================================================
+// PCIe is full duplex and the copy engines run beside the SMs, so a bulk call on host buffers costs
+// max(upload, kernels, download) instead of their sum when it is cut into chunks. Uploads go on one
+// internal stream, downloads on another, the table kernels stay on the caller's stream; events tie
+// them together so the whole call remains ordered on the caller's stream.
+void cuda_ok(cudaError_t status, char const* what)
+{
+  if (status != cudaSuccess) {
+    cudaGetLastError();
+    throw std::runtime_error(std::string{what} + ": " + cudaGetErrorString(status));
+  }
+}
+
+class host_pipeline {
+ public:
+  static constexpr int depth = 3;
+
+  static host_pipeline& for_current_device()
+  {
+    static std::mutex guard;
+    static std::map<int, std::unique_ptr<host_pipeline>> per_device;
+    int device = 0;
+    cuda_ok(cudaGetDevice(&device), "cudaGetDevice");
+    std::lock_guard<std::mutex> lock{guard};
+    auto& slot = per_device[device];
+    if (!slot) { slot.reset(new host_pipeline{}); }
+    return *slot;
+  }
+
+  std::mutex mutex;  ///< one host-buffer call at a time per device (they share the staging buffers)
+  cudaStream_t upload{}, download{};
+  cudaEvent_t forked{}, uploaded[depth]{}, consumed[depth]{}, produced[depth]{}, downloaded[depth]{};
+  char* in[depth]{};
+  char* out[depth]{};
+  std::size_t in_bytes{0}, out_bytes{0};
+
+  void reserve(std::size_t in_need, std::size_t out_need)
+  {
+    if (in_need > in_bytes) {
+      cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+      for (auto& b : in) {
+        if (b) { cudaFree(b); }
+        b = nullptr;
+        cuda_ok(cudaMalloc(reinterpret_cast<void**>(&b), in_need), "cudaMalloc(host pipeline input)");
+      }
+      in_bytes = in_need;
+    }
+    if (out_need > out_bytes) {
+      cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+      for (auto& b : out) {
+        if (b) { cudaFree(b); }
+        b = nullptr;
+        cuda_ok(cudaMalloc(reinterpret_cast<void**>(&b), out_need), "cudaMalloc(host pipeline output)");
+      }
+      out_bytes = out_need;
+    }
+  }
+
+ private:
+  host_pipeline()
+  {
+    cuda_ok(cudaStreamCreateWithFlags(&upload, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_ok(cudaStreamCreateWithFlags(&download, cudaStreamNonBlocking), "cudaStreamCreate");
+    auto make = [](cudaEvent_t& e) {
+      cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    };
+    make(forked);
+    for (int i = 0; i < depth; ++i) {
+      make(uploaded[i]);
+      make(consumed[i]);
+      make(produced[i]);
+      make(downloaded[i]);
+    }
+  }
+};
+
+std::int64_t host_chunk_elements()
+{
+  static std::int64_t const value = [] {
+    if (char const* s = std::getenv("CUCO_B200_HOST_CHUNK")) {
+      auto const v = std::atoll(s);
+      if (v > 0) { return static_cast<std::int64_t>(v); }
+    }
+    return std::int64_t{1} << 22;  // 4 Mi elements: 64 MB of int64 pairs, ~1.2 ms of PCIe 5 x16
+  }();
+  return value;
+}
+
+std::size_t align256(std::size_t bytes) { return (bytes + 255) / 256 * 256; }
+
+/// Runs `op(device_keys, device_values, device_out, count)` chunk by chunk over host buffers.
+/// in_a / in_b: host arrays with `a_bytes` / `b_bytes` per element (in_b may be null);
+/// host_out: host array with `out_elem` bytes per element (may be null: no download).
+template <typename Op>
+void run_host_pipeline(const void* in_a,
+                       std::size_t a_bytes,
+                       const void* in_b,
+                       std::size_t b_bytes,
+                       void* host_out,
+                       std::size_t out_elem,
+                       void* host_out2,
+                       std::size_t out2_elem,
+                       std::int64_t n,
+                       cudaStream_t stream,
+                       Op&& op)
+{
+  if (n == 0) { return; }
+  auto& pipe = host_pipeline::for_current_device();
+  std::lock_guard<std::mutex> lock{pipe.mutex};
+  std::int64_t const chunk = std::min<std::int64_t>(host_chunk_elements(), n);
+  std::size_t const b_off   = align256(static_cast<std::size_t>(chunk) * a_bytes);
+  std::size_t const out2_off = align256(static_cast<std::size_t>(chunk) * out_elem);
+  pipe.reserve(b_off + align256(static_cast<std::size_t>(chunk) * b_bytes),
+               out2_off + align256(static_cast<std::size_t>(chunk) * out2_elem));
+
+  // uploads start after whatever the caller has already queued on `stream`
+  cuda_ok(cudaEventRecord(pipe.forked, stream), "cudaEventRecord");
+  cuda_ok(cudaStreamWaitEvent(pipe.upload, pipe.forked, 0), "cudaStreamWaitEvent");
+  bool const downloads = host_out != nullptr;
+
+  std::int64_t index = 0;
+  for (std::int64_t begin = 0; begin < n; begin += chunk, ++index) {
+    int const b             = static_cast<int>(index % host_pipeline::depth);
+    std::int64_t const count = std::min<std::int64_t>(chunk, n - begin);
+    // staging buffer b is free once the kernels of its previous chunk have run
+    cuda_ok(cudaStreamWaitEvent(pipe.upload, pipe.consumed[b], 0), "cudaStreamWaitEvent");
+    cuda_ok(cudaMemcpyAsync(pipe.in[b],
+                            static_cast<char const*>(in_a) + static_cast<std::size_t>(begin) * a_bytes,
+                            static_cast<std::size_t>(count) * a_bytes,
+                            cudaMemcpyHostToDevice,
+                            pipe.upload),
+            "cudaMemcpyAsync(H2D)");
+    if (in_b != nullptr) {
+      cuda_ok(cudaMemcpyAsync(pipe.in[b] + b_off,
+                              static_cast<char const*>(in_b) + static_cast<std::size_t>(begin) * b_bytes,
+                              static_cast<std::size_t>(count) * b_bytes,
+                              cudaMemcpyHostToDevice,
+                              pipe.upload),
+              "cudaMemcpyAsync(H2D)");
+    }
+    cuda_ok(cudaEventRecord(pipe.uploaded[b], pipe.upload), "cudaEventRecord");
+
+    cuda_ok(cudaStreamWaitEvent(stream, pipe.uploaded[b], 0), "cudaStreamWaitEvent");
+    if (downloads) {
+      cuda_ok(cudaStreamWaitEvent(stream, pipe.downloaded[b], 0), "cudaStreamWaitEvent");
+    }
+    op(pipe.in[b], in_b != nullptr ? pipe.in[b] + b_off : nullptr, pipe.out[b], pipe.out[b] + out2_off, count);
+    cuda_ok(cudaEventRecord(pipe.consumed[b], stream), "cudaEventRecord");
+
+    if (downloads) {
+      cuda_ok(cudaStreamWaitEvent(pipe.download, pipe.consumed[b], 0), "cudaStreamWaitEvent");
+      cuda_ok(cudaMemcpyAsync(static_cast<char*>(host_out) + static_cast<std::size_t>(begin) * out_elem,
+                              pipe.out[b],
+                              static_cast<std::size_t>(count) * out_elem,
+                              cudaMemcpyDeviceToHost,
+                              pipe.download),
+              "cudaMemcpyAsync(D2H)");
+      if (host_out2 != nullptr) {
+        cuda_ok(cudaMemcpyAsync(static_cast<char*>(host_out2) + static_cast<std::size_t>(begin) * out2_elem,
+                                pipe.out[b] + out2_off,
+                                static_cast<std::size_t>(count) * out2_elem,
+                                cudaMemcpyDeviceToHost,
+                                pipe.download),
+                "cudaMemcpyAsync(D2H)");
+      }
+      cuda_ok(cudaEventRecord(pipe.downloaded[b], pipe.download), "cudaEventRecord");
+    }
+  }
+  if (downloads) {
+    // the call is complete on `stream` only when every result has reached the host
+    for (int b = 0; b < host_pipeline::depth; ++b) {
+      cuda_ok(cudaStreamWaitEvent(stream, pipe.downloaded[b], 0), "cudaStreamWaitEvent");
+    }
+  }
+}
+
 }  // namespace
 
 // everything else in the library is built with -fvisibility=hidden; the C ABI is the export list
@@ -415,6 +599,80 @@ int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream)
   });
 }
 
+int cuco_b200_insert_host(cuco_b200_table* t,
+                          const void* host_keys,
+                          const void* host_values,
+                          int64_t n,
+                          void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (host_keys || n == 0), "bad argument");
+    auto const kb = static_cast<std::size_t>(t->key_bytes());
+    auto const vb = static_cast<std::size_t>(t->value_bytes());
+    bool const aos = vb != 0 && host_values == nullptr;
+    run_host_pipeline(host_keys, aos ? kb + vb : kb, host_values, vb, nullptr, 0, nullptr, 0, n,
+                      static_cast<cudaStream_t>(stream),
+                      [&](void* keys, void* values, void*, void*, std::int64_t count) {
+                        t->insert(keys, values, count, stream, nullptr);
+                        check_launch();
+                      });
+  });
+}
+
+int cuco_b200_find_host(
+  cuco_b200_table* t, const void* host_keys, void* host_out, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((host_keys && host_out) || n == 0), "bad argument");
+    auto const kb  = static_cast<std::size_t>(t->key_bytes());
+    auto const out = static_cast<std::size_t>(t->value_bytes() ? t->value_bytes() : t->key_bytes());
+    run_host_pipeline(host_keys, kb, nullptr, 0, host_out, out, nullptr, 0, n,
+                      static_cast<cudaStream_t>(stream),
+                      [&](void* keys, void*, void* found, void*, std::int64_t count) {
+                        t->find(keys, found, count, stream);
+                        check_launch();
+                      });
+  });
+}
+
+int cuco_b200_contains_host(
+  cuco_b200_table* t, const void* host_keys, uint8_t* host_out, int64_t n, void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((host_keys && host_out) || n == 0), "bad argument");
+    auto const kb = static_cast<std::size_t>(t->key_bytes());
+    run_host_pipeline(host_keys, kb, nullptr, 0, host_out, 1, nullptr, 0, n,
+                      static_cast<cudaStream_t>(stream),
+                      [&](void* keys, void*, void* present, void*, std::int64_t count) {
+                        t->contains(keys, static_cast<std::uint8_t*>(present), count, stream);
+                        check_launch();
+                      });
+  });
+}
+
+int cuco_b200_insert_and_find_host(cuco_b200_table* t,
+                                   const void* host_keys,
+                                   const void* host_values,
+                                   void* host_found,
+                                   uint8_t* host_inserted,
+                                   int64_t n,
+                                   void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((host_keys && host_found && host_inserted) || n == 0), "bad argument");
+    auto const kb  = static_cast<std::size_t>(t->key_bytes());
+    auto const vb  = static_cast<std::size_t>(t->value_bytes());
+    bool const aos = vb != 0 && host_values == nullptr;
+    auto const out = vb ? vb : kb;
+    run_host_pipeline(host_keys, aos ? kb + vb : kb, host_values, vb, host_found, out, host_inserted, 1, n,
+                      static_cast<cudaStream_t>(stream),
+                      [&](void* keys, void* values, void* found, void* inserted, std::int64_t count) {
+                        t->insert_and_find(keys, values, found, static_cast<std::uint8_t*>(inserted), count, stream);
+                        check_launch();
+                      });
+  });
+}
+
 int cuco_b200_set_tuning(int keys_per_thread,
                          int cas_first,
                          int sector_chunks,
@@ -456,6 +714,23 @@ int cuco_b200_set_blocking(int mode, int region_mib)
   auto& t   = cuco::b200::tuning();
   t.blocked = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
   if (region_mib > 0) { t.region_bytes = static_cast<std::size_t>(region_mib) << 20; }
+  if (region_mib < 0) { t.region_bytes = static_cast<std::size_t>(-region_mib) << 10; }  // KiB (tests)
+  return 0;
+#endif
+}
+
+int cuco_b200_set_blocking_variant(int keys_per_thread, int cas_first, int prefetch)
+{
+#if defined(CUCO_SHIM_REFERENCE)
+  (void)keys_per_thread, (void)cas_first, (void)prefetch;
+  return 1;
+#else
+  auto& t = cuco::b200::tuning();
+  if (keys_per_thread == 1 || keys_per_thread == 2 || keys_per_thread == 4) {
+    t.blocked_keys_per_thread = keys_per_thread;
+  }
+  if (cas_first >= 0) { t.blocked_cas_first = cas_first != 0; }
+  if (prefetch >= 0) { t.blocked_prefetch = prefetch != 0; }
   return 0;
 #endif
 }

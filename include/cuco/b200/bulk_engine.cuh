@@ -57,9 +57,12 @@ struct tuning_t {
   bool l2_window       = true;  ///< persisting-L2 access window for tables <= l2_window_bytes
   bool coherent_loads  = false; ///< mutating kernels read the table with relaxed.gpu loads
   int blocked          = -1;    ///< L2-blocked mutations: -1 auto (tables much larger than L2), 0 off, 1 on
-  std::size_t region_bytes          = std::size_t{32} << 20;   ///< table slice kept L2-resident
-  std::size_t blocked_min_table     = std::size_t{192} << 20;  ///< auto mode: table at least this big
+  std::size_t region_bytes          = std::size_t{16} << 20;   ///< table slice kept L2-resident
+  std::size_t blocked_min_table     = std::size_t{256} << 20;  ///< auto mode: table at least this big
   std::int64_t blocked_min_elements = std::int64_t{1} << 22;   ///< auto mode: batch at least this big
+  int blocked_keys_per_thread = 2;  ///< pass 2 of the blocked path: probes in flight per thread
+  bool blocked_cas_first      = false;  ///< pass 2 starts with the CAS (table slice is L2-resident)
+  bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
   std::size_t l2_window_bytes = std::size_t{48} << 20;
 };
 
@@ -75,6 +78,9 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_L2_WINDOW")) { t.l2_window = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_COHERENT")) { t.coherent_loads = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_BLOCKED")) { t.blocked = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_BLOCKED_KPT")) { t.blocked_keys_per_thread = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_BLOCKED_CAS_FIRST")) { t.blocked_cas_first = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_BLOCKED_PREFETCH")) { t.blocked_prefetch = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
     t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
   }
@@ -87,15 +93,6 @@ inline tuning_t& tuning()
   static tuning_t t = tuning_from_env();
   return t;
 }
-
-/// Identity predicate for the un-stencilled entry points.
-struct always_true {
-  template <typename T>
-  __host__ __device__ constexpr bool operator()(T const&) const noexcept
-  {
-    return true;
-  }
-};
 
 /// Grid for a persistent kernel: resident CTAs on the device times `waves`, capped by the tiles.
 template <typename Kernel>
@@ -722,14 +719,18 @@ class table_engine {
     launch(kernel, generic_grid(n), block_size, stream.get(), base, window, in, n, st, pred, counter, engine, action);
   }
 
-  /// Should this batch take the L2-blocked path?
+  /// Should this batch take the L2-blocked path? Auto mode wants a table well beyond L2, a batch
+  /// that touches it about once per 64 bytes or denser (otherwise there is no line reuse to win),
+  /// and regions that still fit L2 with the region count capped.
   [[nodiscard]] bool blocking_pays(cuco::detail::index_type n) const noexcept
   {
     auto const& t = tuning();
-    if (t.blocked == 0) { return false; }
-    if (t.blocked > 0) { return n > 0; }
+    if (t.blocked == 0 || n <= 0) { return false; }
     auto const bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
-    return bytes >= t.blocked_min_table && n >= t.blocked_min_elements;
+    if (bytes / route_max_regions > (std::size_t{48} << 20)) { return false; }
+    if (t.blocked > 0) { return true; }
+    return bytes >= t.blocked_min_table && n >= t.blocked_min_elements &&
+           static_cast<std::size_t>(n) * 64 >= bytes;
   }
 
   /// Grow-only staging memory owned by the container (avoids a malloc/free per bulk call).
@@ -745,8 +746,8 @@ class table_engine {
     return scratch_;
   }
 
-  /// L2-blocked mutation: route the batch by table region (pass 1), then run the ordinary mutate
-  /// kernel over the regions in order (pass 2). See bulk_kernels.cuh, "L2-blocked mutation".
+  /// L2-blocked mutation: route the batch by table region (pass 1), then probe the regions in
+  /// order with the region's slots resident in L2 (pass 2). See bulk_kernels.cuh.
   template <bool Counted, typename InputIt, typename EngineT, typename Action>
   void blocked_mutate(InputIt in,
                       cuco::detail::index_type n,
@@ -764,10 +765,10 @@ class table_engine {
     // expected elements per region plus 1/16 slack and a constant for tiny batches
     auto const mean             = (static_cast<std::uint64_t>(n) + num_regions - 1) / num_regions;
     auto const segment_capacity = static_cast<std::uint32_t>(mean + mean / 16 + 1024);
-    auto const virtual_n        = static_cast<index_type>(num_regions) * segment_capacity;
+    auto const staged           = static_cast<std::uint64_t>(num_regions) * segment_capacity;
 
     std::size_t const counts_bytes = ((num_regions * sizeof(unsigned int)) + 255) / 256 * 256;
-    auto* base     = static_cast<char*>(this->scratch(counts_bytes + virtual_n * sizeof(value_type)));
+    auto* base     = static_cast<char*>(this->scratch(counts_bytes + staged * sizeof(value_type)));
     auto* counts   = reinterpret_cast<unsigned int*>(base);
     auto* segments = reinterpret_cast<value_type*>(base + counts_bytes);
     cudaMemsetAsync(counts, 0, num_regions * sizeof(unsigned int), stream.get());
@@ -777,38 +778,50 @@ class table_engine {
 
     constexpr int chunk = EngineT::sector_chunk_slots;
     {
-      auto const kernel  = route_kernel<block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
-      auto const tiles   = cuco::detail::int_div_ceil(n, index_type{block_size} * route_items_per_thread);
-      std::size_t const smem = 2 * num_regions * sizeof(unsigned int);
-      auto const grid = static_cast<unsigned>(
-        std::min<index_type>(tiles, index_type{cuco::detail::multiprocessor_count()} * 4));
+      auto const kernel = route_kernel<block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
+      constexpr std::size_t smem = route_smem_bytes<block_size, value_type>();
+      static bool const configured = [&] {
+        return cudaFuncSetAttribute(
+                 kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+      }();
+      (void)configured;
+      auto const tiles = cuco::detail::int_div_ceil(n, index_type{block_size} * route_items_per_thread);
+      auto const grid  = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
       kernel<<<grid, block_size, smem, stream.get()>>>(
         in, n, segments, counts, regions, segment_capacity, counter, engine, action);
     }
     {
-      auto const stencil = thrust::counting_iterator<index_type>{0};
-      auto const live    = segment_live{counts, segment_capacity};
-      auto const* first  = static_cast<value_type const*>(segments);
-      auto run           = [&](auto kpt, auto chunk_tag) {
-        constexpr int KPT   = decltype(kpt)::value;
-        constexpr int Chunk = decltype(chunk_tag)::value;
-        auto const kernel   = mutate_kernel<block_size,
-                                          KPT,
-                                          Chunk,
-                                          false,
-                                          Counted,
-                                          load_policy::streaming,
-                                          value_type const*,
-                                          thrust::counting_iterator<index_type>,
-                                          segment_live,
-                                          size_type,
-                                          EngineT,
-                                          Action>;
-        auto const tiles = cuco::detail::int_div_ceil(virtual_n, index_type{block_size} * KPT);
-        kernel<<<persistent_grid(kernel, block_size, tiles), block_size, 0, stream.get()>>>(
-          first, virtual_n, stencil, live, counter, engine, action);
+      auto run = [&](auto kpt, auto cas_first) {
+        constexpr int KPT       = decltype(kpt)::value;
+        constexpr bool CasFirst = decltype(cas_first)::value;
+        auto const kernel =
+          blocked_mutate_kernel<block_size, KPT, chunk, CasFirst, Counted, size_type, EngineT, Action>;
+        auto const tiles_per_segment = static_cast<unsigned>(
+          cuco::detail::int_div_ceil(index_type{segment_capacity}, index_type{block_size} * KPT));
+        auto const region_slots = (capacity + num_regions - 1) / num_regions;
+        auto const region_bytes = region_slots * sizeof(value_type);
+        auto const share        = (region_bytes + tiles_per_segment - 1) / tiles_per_segment;
+        blocked_layout const layout{
+          counts,
+          segment_capacity,
+          region_slots,
+          table_bytes,
+          t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u};
+        kernel<<<dim3{tiles_per_segment, num_regions}, block_size, 0, stream.get()>>>(
+          segments, layout, counter, engine, action);
       };
-      dispatch_variant<EngineT, true>(run);
+#if defined(CUCO_B200_TUNABLE)
+      auto with_kpt = [&](auto cas_first) {
+        switch (t.blocked_keys_per_thread) {
+          case 1: run(std::integral_constant<int, 1>{}, cas_first); break;
+          case 4: run(std::integral_constant<int, 4>{}, cas_first); break;
+          default: run(std::integral_constant<int, 2>{}, cas_first); break;
+        }
+      };
+      t.blocked_cas_first ? with_kpt(std::true_type{}) : with_kpt(std::false_type{});
+#else
+      run(std::integral_constant<int, 2>{}, std::false_type{});
+#endif
     }
   }
 

@@ -28,6 +28,7 @@
 
 #include <cuda/atomic>
 #include <cuda/std/iterator>
+#include <thrust/iterator/constant_iterator.h>
 #include <thrust/iterator/iterator_traits.h>
 
 #include <cooperative_groups.h>
@@ -38,6 +39,15 @@
 namespace cuco::b200 {
 
 using cuco::detail::index_type;
+
+/// Identity predicate for the un-stencilled entry points.
+struct always_true {
+  template <typename T>
+  __host__ __device__ constexpr bool operator()(T const&) const noexcept
+  {
+    return true;
+  }
+};
 
 /// Reads element `i` of an input range; raw pointers take the streaming (read-once) path.
 template <typename It>
@@ -132,18 +142,23 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void lookup_kernel(InputIt first,
     cursor cur[KeysPerThread];
     unsigned pending = 0;
 
+    // all input loads are posted before the first one is consumed (the loads are volatile asm:
+    // hashing key j inside the same loop would serialise the DRAM round trips)
 #pragma unroll
     for (int j = 0; j < KeysPerThread; ++j) {
       index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
       if (idx < n) {
         if (pred(*(stencil + idx))) {
           key[j].value = read_input(first, idx);
-          cur[j]       = engine.make_cursor(key[j].value);
           pending |= 1u << j;
         } else {
           *(out + idx) = emit.miss();
         }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (pending & (1u << j)) { cur[j] = engine.make_cursor(key[j].value); }
     }
 
     while (pending) {
@@ -337,25 +352,25 @@ __device__ bool mutate_slow_path(
   return res.second;
 }
 
+/// One tile of the fast mutation path: element j of thread t is `tile_base + j * BlockSize + t`, live
+/// while that index is below `limit` and its stencil passes. Returns the number of new keys.
 template <int BlockSize,
           int KeysPerThread,
           int ChunkSlots,
           bool CasFirst,
-          bool Counted,
           load_policy Policy,
           typename InputIt,
           typename StencilIt,
           typename Predicate,
-          typename Counter,
           typename Engine,
           typename Action>
-CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
-                                                            index_type n,
-                                                            StencilIt stencil,
-                                                            Predicate pred,
-                                                            Counter* num_new,
-                                                            Engine engine,
-                                                            Action action)
+__device__ __forceinline__ unsigned long long mutate_tile(InputIt first,
+                                                          index_type tile_base,
+                                                          index_type limit,
+                                                          StencilIt stencil,
+                                                          Predicate& pred,
+                                                          Engine& engine,
+                                                          Action& action)
 {
   using slot_type = typename Engine::value_type;
   using key_type  = typename Engine::key_type;
@@ -364,31 +379,33 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
   // invoked on it, exactly where the reference invokes them; the slot image is derived on demand
   using input_type = decltype(engine.heterogeneous_value(read_input(first, index_type{0})));
   static_assert(Engine::single_cas, "fast mutate path needs one-shot claimable slots");
-  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
-  constexpr auto policy     = Policy;
+  constexpr auto policy = Policy;
   // claim only the key half, then combine the payload in place (insert_or_apply direct mode)
   constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
 
-  auto* const table      = engine.slots();
-  auto const empty_slot  = engine.empty_slot_sentinel();
+  auto* const table       = engine.slots();
+  auto const empty_slot   = engine.empty_slot_sentinel();
+  index_type const n      = limit;
   unsigned long long mine = 0;
-
-  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
-       tile_base += index_type{gridDim.x} * tile) {
+  {
     uninitialized<input_type> val[KeysPerThread];
     cursor cur[KeysPerThread];
     unsigned pending = 0;  // bit j: key j still in flight
     unsigned claim   = 0;  // bit j: next action of key j is a CAS at cur[j].slot (else a chunk load)
 
+    // post every input load before consuming the first (see lookup_kernel)
 #pragma unroll
     for (int j = 0; j < KeysPerThread; ++j) {
       index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
       if (idx < n && pred(*(stencil + idx))) {
         val[j].value = engine.heterogeneous_value(read_input(first, idx));
-        cur[j]       = engine.make_cursor(Engine::key_of(val[j].value));
         pending |= 1u << j;
         if constexpr (CasFirst) { claim |= 1u << j; }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (pending & (1u << j)) { cur[j] = engine.make_cursor(Engine::key_of(val[j].value)); }
     }
 
     while (pending) {
@@ -479,7 +496,36 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
       }
     }
   }
+  return mine;
+}
 
+template <int BlockSize,
+          int KeysPerThread,
+          int ChunkSlots,
+          bool CasFirst,
+          bool Counted,
+          load_policy Policy,
+          typename InputIt,
+          typename StencilIt,
+          typename Predicate,
+          typename Counter,
+          typename Engine,
+          typename Action>
+CUCO_KERNEL __launch_bounds__(BlockSize) void mutate_kernel(InputIt first,
+                                                            index_type n,
+                                                            StencilIt stencil,
+                                                            Predicate pred,
+                                                            Counter* num_new,
+                                                            Engine engine,
+                                                            Action action)
+{
+  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
+  unsigned long long mine   = 0;
+  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
+       tile_base += index_type{gridDim.x} * tile) {
+    mine += mutate_tile<BlockSize, KeysPerThread, ChunkSlots, CasFirst, Policy>(
+      first, tile_base, n, stencil, pred, engine, action);
+  }
   if constexpr (Counted) { accumulate_count(num_new, mine); }
 }
 
@@ -544,24 +590,31 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void generic_mutate_kernel(InputIt firs
 }
 
 // =================================================================================================
-// L2-blocked mutation, pass 1: route the batch by table region
+// L2-blocked mutation: route the batch by table region, then probe region by region
 // =================================================================================================
 //
-// Measured on B200 (tools/microbench.cu): an L2 miss to a random table sector costs the same
-// whether 16 or 128 bytes are wanted - about 37.9 G misses/s chip-wide, every one fetching a 128-byte
-// line - while sectors that are already in the 126 MB L2 are served at ~280 G/s. A mutation on a
-// table larger than L2 therefore pays one DRAM line fetch per key plus one write-back per new key,
-// and that, not the probing code, bounds cuco-style insertion at ~23 Gops/s.
+// Measured on B200 (tools/microbench*.cu, profiles/r01_hardware_probes.md):
+//   * an L2 miss to a random table sector moves a whole 128-byte line from DRAM (3.9 sectors per
+//     32-byte read), so random probing tops out near 49 G reads/s and ~22 G read+CAS/s chip-wide;
+//   * the same number of accesses confined to one 16-32 MB slice of the table at a time run at
+//     174 G reads/s and 55-60 G read+CAS/s: the slice is fetched line by line exactly once, the
+//     other three sectors of every line are hits, and dirty sectors leave L2 once.
+// A mutation batch that touches a table far larger than L2 about once per sector is therefore ~3x
+// cheaper when it arrives grouped by table region, and a shared-memory staged partition of the
+// batch costs about one streaming read + write of it.
 //
-// The blocked path spends two streaming passes to get rid of almost all of those misses: pass 1
-// (this kernel) scatters the batch into per-region segments of a scratch buffer, a region being a
-// contiguous slice of the slot array of about 32 MB; pass 2 runs the ordinary mutate kernel over the
-// segments in region order, so at any time the keys in flight target one or two regions that stay
-// resident in L2. Every table line is then fetched from DRAM once per batch instead of once per key.
+// Pass 1 (`route_kernel`): every CTA takes a tile of the batch, ranks its elements per region with
+// shared-memory counters, reserves a run in each region's segment with ONE global atomic per
+// (tile, region), stages the tile in shared memory grouped by region and copies it out in runs that
+// are contiguous in both shared and global memory (full 128-byte lines instead of scattered 16-byte
+// stores). Segments have a fixed capacity (expected load + slack); an element whose segment is
+// full is finished right there through the general driver, which keeps the path correct for
+// arbitrarily skewed inputs without a counting pre-pass.
 //
-// Segments have a fixed capacity (expected load + slack); an element whose segment is full is
-// finished right here through the general driver, which keeps the path correct for arbitrarily
-// skewed inputs without a counting pre-pass.
+// Pass 2 (`blocked_mutate_kernel`): grid (tiles per segment, regions), so CTAs are dispatched
+// region by region; each CTA runs the ordinary tile body (`mutate_tile`) on its slice of one
+// segment, after posting one bulk L2 prefetch of its share of the NEXT region's table slice
+// (`cp.async.bulk.prefetch.L2`), which turns that region's first touches into L2 hits.
 
 /// Maps a home slot to its region: floor(slot * num_regions / capacity) by multiply-high.
 struct region_map {
@@ -579,21 +632,15 @@ struct region_map {
   }
 };
 
-/// Pass-2 predicate: virtual element i of the segmented scratch buffer exists.
-struct segment_live {
-  unsigned int const* counts;  ///< elements stored per region (may exceed segment_capacity: clamped)
-  std::uint32_t segment_capacity;
+constexpr int route_items_per_thread = 16;
+constexpr int route_max_regions      = 1024;
 
-  __device__ bool operator()(index_type i) const noexcept
-  {
-    auto const region = static_cast<std::uint32_t>(i / segment_capacity);
-    auto const local  = static_cast<std::uint32_t>(i - index_type{region} * segment_capacity);
-    return local < counts[region];
-  }
-};
-
-constexpr int route_items_per_thread = 8;
-constexpr int route_max_regions      = 2048;
+/// Dynamic shared memory of `route_kernel` for a slot type.
+template <int BlockSize, typename Slot>
+constexpr std::size_t route_smem_bytes() noexcept
+{
+  return std::size_t{BlockSize} * route_items_per_thread * (sizeof(Slot) + sizeof(std::uint16_t));
+}
 
 template <int BlockSize,
           int ChunkSlots,
@@ -604,7 +651,7 @@ template <int BlockSize,
           typename Action>
 CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
                                                            index_type n,
-                                                           typename Engine::value_type* scratch,
+                                                           typename Engine::value_type* segments,
                                                            unsigned int* region_counts,
                                                            region_map regions,
                                                            std::uint32_t segment_capacity,
@@ -613,59 +660,275 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
                                                            Action action)
 {
   using slot_type = typename Engine::value_type;
-  extern __shared__ unsigned int route_smem[];
-  unsigned int* const tile_hist = route_smem;                         // [num_regions]
-  unsigned int* const tile_base = route_smem + regions.num_regions;   // [num_regions]
-  constexpr index_type tile = index_type{BlockSize} * route_items_per_thread;
-  unsigned long long mine   = 0;
+  constexpr int items          = route_items_per_thread;
+  constexpr index_type tile    = index_type{BlockSize} * items;
+  constexpr int regions_per_thread = (route_max_regions + BlockSize - 1) / BlockSize;
+
+  extern __shared__ __align__(16) unsigned char route_dynamic_smem[];
+  auto* const stage = reinterpret_cast<slot_type*>(route_dynamic_smem);            // [tile]
+  auto* const owner = reinterpret_cast<std::uint16_t*>(stage + tile);              // [tile]
+  __shared__ unsigned int tile_hist[route_max_regions];    // elements of this tile per region
+  __shared__ unsigned int tile_start[route_max_regions];   // first staged position of the region
+  __shared__ unsigned int run_start[route_max_regions];    // reserved position in the segment
+  __shared__ unsigned int warp_sums[BlockSize / 32];
+
+  std::uint32_t const num_regions = regions.num_regions;
+  unsigned long long mine         = 0;
 
   for (index_type base = index_type{blockIdx.x} * tile; base < n;
        base += index_type{gridDim.x} * tile) {
-    for (std::uint32_t r = threadIdx.x; r < regions.num_regions; r += BlockSize) {
+    for (std::uint32_t r = threadIdx.x; r < num_regions; r += BlockSize) {
       tile_hist[r] = 0;
     }
     __syncthreads();
 
-    slot_type image[route_items_per_thread];
-    std::uint32_t region[route_items_per_thread];
-    std::uint32_t rank[route_items_per_thread];
+    using input_type = decltype(engine.heterogeneous_value(read_input(first, index_type{0})));
+    uninitialized<input_type> val[items];
+    std::uint32_t region[items];
+    std::uint32_t rank[items];
+    // all loads of the tile in flight first; hashing starts when the first one lands
 #pragma unroll
-    for (int j = 0; j < route_items_per_thread; ++j) {
+    for (int j = 0; j < items; ++j) {
+      index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
+      if (idx < n) { val[j].value = engine.heterogeneous_value(read_input(first, idx)); }
+    }
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
       index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
       region[j]            = 0xffffffffu;
-      if (idx < n) {
-        auto const val = engine.heterogeneous_value(read_input(first, idx));
-        image[j]       = engine.native_value(val);
-        region[j]      = regions(engine.make_cursor(Engine::key_of(val)).slot);
-      }
-      // one shared-memory atomic per distinct region per warp
-      unsigned const peers  = __match_any_sync(0xffffffffu, region[j]);
-      int const leader      = __ffs(peers) - 1;
-      unsigned const before = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
-      unsigned start        = 0;
-      if (region[j] != 0xffffffffu && leader == static_cast<int>(threadIdx.x & 31)) {
-        start = atomicAdd(&tile_hist[region[j]], __popc(peers));
-      }
-      rank[j] = __shfl_sync(0xffffffffu, start, leader) + before;
+      if (idx < n) { region[j] = regions(engine.make_cursor(Engine::key_of(val[j].value)).slot); }
     }
-    __syncthreads();
-    for (std::uint32_t r = threadIdx.x; r < regions.num_regions; r += BlockSize) {
-      tile_base[r] = tile_hist[r] ? atomicAdd(&region_counts[r], tile_hist[r]) : 0u;
-    }
-    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < route_items_per_thread; ++j) {
-      if (region[j] == 0xffffffffu) { continue; }
-      auto const pos = static_cast<std::uint64_t>(tile_base[region[j]]) + rank[j];
-      if (pos < segment_capacity) {
-        scratch[static_cast<std::uint64_t>(region[j]) * segment_capacity + pos] = image[j];
+    for (int j = 0; j < items; ++j) {
+      if (region[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[region[j]], 1u); }
+    }
+    __syncthreads();
+
+    // exclusive scan of the tile histogram; thread t owns regions [t * rpt, (t + 1) * rpt)
+    {
+      unsigned int held[regions_per_thread];
+      unsigned int sum = 0;
+#pragma unroll
+      for (int i = 0; i < regions_per_thread; ++i) {
+        std::uint32_t const r = threadIdx.x * regions_per_thread + i;
+        held[i]               = r < num_regions ? tile_hist[r] : 0u;
+        sum += held[i];
+      }
+      unsigned int inclusive = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned int const up = __shfl_up_sync(0xffffffffu, inclusive, d);
+        if ((threadIdx.x & 31) >= d) { inclusive += up; }
+      }
+      if ((threadIdx.x & 31) == 31) { warp_sums[threadIdx.x >> 5] = inclusive; }
+      __syncthreads();
+      unsigned int running = inclusive - sum;
+      for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) {
+        running += warp_sums[w];
+      }
+#pragma unroll
+      for (int i = 0; i < regions_per_thread; ++i) {
+        std::uint32_t const r = threadIdx.x * regions_per_thread + i;
+        if (r < num_regions) {
+          tile_start[r] = running;
+          run_start[r]  = held[i] ? atomicAdd(&region_counts[r], held[i]) : 0u;
+          running += held[i];
+        }
+      }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      if (region[j] != 0xffffffffu) {
+        unsigned int const pos = tile_start[region[j]] + rank[j];
+        stage[pos]             = engine.native_value(val[j].value);
+        owner[pos]             = static_cast<std::uint16_t>(region[j]);
+      }
+    }
+    __syncthreads();
+
+    auto const count = static_cast<unsigned int>((n - base) < tile ? (n - base) : tile);
+    for (unsigned int pos = threadIdx.x; pos < count; pos += BlockSize) {
+      std::uint32_t const r     = owner[pos];
+      std::uint64_t const where = std::uint64_t{run_start[r]} + (pos - tile_start[r]);
+      if (where < segment_capacity) {
+        segments[std::uint64_t{r} * segment_capacity + where] = stage[pos];
       } else {
         // segment full (heavily skewed input): finish this element now, unblocked
-        index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
-        mine += mutate_slow_path<ChunkSlots, load_policy::streaming>(engine, image[j], idx, action);
+        mine += mutate_slow_path<ChunkSlots, load_policy::streaming>(
+          engine, stage[pos], base + pos, action);
       }
     }
     __syncthreads();
+  }
+  if constexpr (Counted) { accumulate_count(num_new, mine); }
+}
+
+/// Geometry of pass 2, shared by host and device.
+struct blocked_layout {
+  unsigned int const* counts;       ///< elements routed to each region (may exceed the capacity)
+  std::uint32_t segment_capacity;   ///< elements a segment can hold
+  std::uint64_t region_slots;       ///< ceil(capacity / num_regions): slots per region
+  std::uint64_t table_bytes;        ///< end of the slot array (prefetch clamp)
+  std::uint32_t prefetch_bytes;     ///< per-CTA share of the next region (multiple of 128), 0 = off
+};
+
+template <int BlockSize,
+          int KeysPerThread,
+          int ChunkSlots,
+          bool CasFirst,
+          bool Counted,
+          typename Counter,
+          typename Engine,
+          typename Action>
+CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
+  typename Engine::value_type const* segments,
+  blocked_layout layout,
+  Counter* num_new,
+  Engine engine,
+  Action action)
+{
+  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
+  std::uint32_t const region = blockIdx.y;
+
+  if (layout.prefetch_bytes != 0 && threadIdx.x == 0 && region + 1 < gridDim.y) {
+    // stream this CTA's share of the next region's slots into L2 while this region is probed
+    std::uint64_t const begin = (std::uint64_t{region} + 1) * layout.region_slots * Engine::slot_bytes +
+                                std::uint64_t{blockIdx.x} * layout.prefetch_bytes;
+    std::uint64_t const limit = (std::uint64_t{region} + 2) * layout.region_slots * Engine::slot_bytes;
+    std::uint64_t end = begin + layout.prefetch_bytes;
+    if (end > limit) { end = limit; }
+    if (end > (layout.table_bytes & ~std::uint64_t{15})) { end = layout.table_bytes & ~std::uint64_t{15}; }
+    if (begin < end) {
+      auto const* address = reinterpret_cast<char const*>(engine.slots()) + (begin & ~std::uint64_t{15});
+      auto const bytes    = static_cast<std::uint32_t>((end - (begin & ~std::uint64_t{15})) & ~std::uint64_t{15});
+      if (bytes != 0) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(address), "r"(bytes) : "memory");
+      }
+    }
+  }
+
+  auto const stored = layout.counts[region];
+  index_type const count =
+    stored < layout.segment_capacity ? index_type{stored} : index_type{layout.segment_capacity};
+  index_type const tile_base = index_type{blockIdx.x} * tile;
+  if (tile_base >= count) { return; }
+
+  // Straight-line tile body. With the region's slots resident in L2 the kernel is bound by issue
+  // slots and dependent round trips, not DRAM, so the general round loop of `mutate_tile` (bitmask
+  // bookkeeping, divergent re-entry) is replaced by three phases over all keys of the thread -
+  // post the input loads, post the home-sector loads, claim - and whatever is left (sector full of
+  // other keys, lost race, foreign payload image) goes through the general driver afterwards.
+  using slot_type = typename Engine::value_type;
+  using key_type  = typename Engine::key_type;
+  using cursor    = typename Engine::cursor;
+  constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
+  constexpr auto policy         = load_policy::streaming;
+
+  index_type const first_idx = index_type{region} * layout.segment_capacity + tile_base + threadIdx.x;
+  index_type const limit     = index_type{region} * layout.segment_capacity + count;
+  auto* const table          = engine.slots();
+  auto const empty_slot      = engine.empty_slot_sentinel();
+  unsigned long long mine    = 0;
+
+  uninitialized<slot_type> val[KeysPerThread];
+  cursor cur[KeysPerThread];
+  unsigned live = 0, claiming = 0, todo = 0;
+
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    index_type const idx = first_idx + index_type{j} * BlockSize;
+    if (idx < limit) {
+      val[j].value = read_input(segments, idx);
+      live |= 1u << j;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    if (live & (1u << j)) { cur[j] = engine.make_cursor(Engine::key_of(val[j].value)); }
+  }
+
+  slot_type seen[KeysPerThread];
+  if constexpr (CasFirst) {
+    claiming = live;
+  } else {
+    raw_chunk<ChunkSlots * Engine::slot_bytes> raw[KeysPerThread];
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (live & (1u << j)) { raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (!(live & (1u << j))) { continue; }
+      auto const& key = Engine::key_of(val[j].value);
+      int const begin_off =
+        static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
+      int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
+      int state_of    = 0;  // 0: sector exhausted, 1: present, 2: claim at cur[j].slot
+#pragma unroll
+      for (int i = 0; i < ChunkSlots; ++i) {
+        if (state_of == 0 && i >= begin_off && i < begin_off + valid) {
+          auto const slot  = chunk_slot<slot_type>(raw[j], i);
+          auto const state = engine.classify_insert(key, Engine::key_of(slot));
+          if (state == equal_result::EQUAL) {
+            action.on_present(engine,
+                              first_idx + index_type{j} * BlockSize,
+                              table + (cur[j].slot + (i - begin_off)),
+                              slot,
+                              val[j].value);
+            state_of = 1;
+          } else if (state == equal_result::AVAILABLE) {
+            cur[j].slot += i - begin_off;  // stays inside the sector, no wrap
+            state_of = 2;
+          }
+        }
+      }
+      if (state_of == 0) { todo |= 1u << j; }
+      if (state_of == 2) { claiming |= 1u << j; }
+    }
+  }
+
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    if (claiming & (1u << j)) {
+      if constexpr (key_only_claim) {
+        key_type expected_key = Engine::key_of(empty_slot);
+        cuda::atomic_ref<key_type, Engine::thread_scope> key_ref{(table + cur[j].slot)->first};
+        key_ref.compare_exchange_strong(expected_key,
+                                        static_cast<key_type>(Engine::key_of(val[j].value)),
+                                        cuda::memory_order_relaxed);
+        seen[j]       = empty_slot;
+        seen[j].first = expected_key;
+      } else {
+        seen[j] = cas_slot<Engine::thread_scope>(table + cur[j].slot, empty_slot, val[j].value);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    if (!(claiming & (1u << j))) { continue; }
+    index_type const idx = first_idx + index_type{j} * BlockSize;
+    auto* const address  = table + cur[j].slot;
+    bool const won       = key_only_claim
+                             ? same_bits(Engine::key_of(seen[j]), Engine::key_of(empty_slot))
+                             : same_bits(seen[j], empty_slot);
+    if (won) {
+      action.on_new(engine, idx, address, val[j].value);
+      ++mine;
+    } else if (engine.classify_insert(Engine::key_of(val[j].value), Engine::key_of(seen[j])) ==
+               equal_result::EQUAL) {
+      action.on_present(engine, idx, address, seen[j], val[j].value);
+    } else {
+      todo |= 1u << j;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    if (todo & (1u << j)) {
+      mine += mutate_slow_path<ChunkSlots, policy>(
+        engine, val[j].value, first_idx + index_type{j} * BlockSize, action);
+    }
   }
   if constexpr (Counted) { accumulate_count(num_new, mine); }
 }

@@ -149,6 +149,28 @@ int cuco_b200_retrieve_all(
 /* rehash (static_map.cuh:911,931): capacity < 0 keeps the current extent. Synchronises. */
 int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream);
 
+/* ---- host-buffer entry points ------------------------------------------------------------------
+ * Same operations as above with HOST pointers (pinned memory for full PCIe speed; pageable memory
+ * works but copies synchronously). There is no reference counterpart - a cuco user copies the batch
+ * to the device, calls the bulk API and copies the results back; these calls do exactly that, cut
+ * into chunks (CUCO_B200_HOST_CHUNK elements, default 4 Mi) so that the upload of chunk i+1, the
+ * table kernels on chunk i and the download of chunk i-1 overlap. Stream-ordered on `stream`: work
+ * queued before the call is seen, and the results are in host memory once `stream` reaches the end
+ * of the call. `host_values == NULL` for maps means AoS pairs, as in cuco_b200_insert. */
+int cuco_b200_insert_host(
+  cuco_b200_table* t, const void* host_keys, const void* host_values, int64_t n, void* stream);
+int cuco_b200_find_host(
+  cuco_b200_table* t, const void* host_keys, void* host_out, int64_t n, void* stream);
+int cuco_b200_contains_host(
+  cuco_b200_table* t, const void* host_keys, uint8_t* host_out, int64_t n, void* stream);
+int cuco_b200_insert_and_find_host(cuco_b200_table* t,
+                                   const void* host_keys,
+                                   const void* host_values,
+                                   void* host_found,
+                                   uint8_t* host_inserted,
+                                   int64_t n,
+                                   void* stream);
+
 /* Launch tuning of the native build (no-op returning 1 in the reference build).
  * keys_per_thread in {1,2,4} sets lookups and mutations alike, or L + 10*M sets them separately
  * (12 = lookups 2, mutations 1); waves = 0 launches one CTA per tile, k > 0 a persistent grid of
@@ -162,8 +184,12 @@ int cuco_b200_set_tuning(int keys_per_thread,
                          int coherent_loads);
 
 /* L2-blocked mutation control of the native build: mode -1 auto (tables much larger than L2),
- * 0 off, 1 always; region_mib = size of the table slice kept L2-resident (<= 0: unchanged). */
+ * 0 off, 1 always; region_mib = size of the table slice kept L2-resident (0: unchanged; negative: the
+ * size in KiB, so tests can exercise many regions on small tables). */
 int cuco_b200_set_blocking(int mode, int region_mib);
+/* Pass 2 of the blocked path: probes in flight per thread (1, 2, 4), whether a probe starts with the
+ * CAS, whether the next region is prefetched into L2. Negative / other = leave unchanged. */
+int cuco_b200_set_blocking_variant(int keys_per_thread, int cas_first, int prefetch);
 
 /* ---- hash-partitioned multi-GPU support (no reference counterpart) --------------
  * owner(key) = mulhi64(murmur_fmix64(key ^ salt), num_parts): high bits of a mix that is independent

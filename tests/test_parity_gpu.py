@@ -292,15 +292,21 @@ def test_full_size_round_trip_properties(native_lib):
     torch.cuda.empty_cache()
 
 
+BLOCKED_VARIANTS = [  # (region MiB or -KiB, keys per thread, cas_first, prefetch)
+    (1, 2, 0, 1), (-16, 1, 1, 1), (-64, 4, 1, 0), (-16, 4, 0, 1), (-256, 2, 1, 1)]
+
+
+@pytest.mark.parametrize("variant", BLOCKED_VARIANTS)
 @pytest.mark.parametrize("kind", [_cabi.MAP_I64_LP1, _cabi.MAP_I64_DH8, _cabi.MAP_I32_LP4, _cabi.SET_I32_DH4])
-def test_l2_blocked_mutations_match_oracle(kind, native_lib):
+def test_l2_blocked_mutations_match_oracle(kind, variant, native_lib):
     """The routed (L2-blocked) insert / insert_or_assign / insert_or_apply path, forced on for small
-    inputs, including a fully skewed batch that overflows a region segment."""
+    inputs (2 to ~120 regions), including a fully skewed batch that overflows a region segment."""
     k = cb.KINDS[kind]
     is_map = k.value is not None
     n = 60_000
     try:
-        native_lib.set_blocking(1, 1)  # always, 1 MiB regions
+        native_lib.set_blocking(1, variant[0])  # always on
+        native_lib.set_blocking_variant(variant[1], variant[2], variant[3])
         streams = {
             "uniform": keyset(kind, n, 21, hi=n),
             "skewed": np.concatenate([np.full(n - 100, 7, dtype=np.int64), np.arange(100, dtype=np.int64) + 100]),
@@ -316,6 +322,7 @@ def test_l2_blocked_mutations_match_oracle(kind, native_lib):
             assert t.size() == ref.size(), name
             q = np.concatenate([keys[::3], keyset(kind, 1000, 22, hi=8 * n)])
             assert np.array_equal(t.find(dev(q, k.key)).cpu().numpy(), ref.find(q)), name
+            assert t.insert(dk, dv) == 0, name  # second pass through the blocked path: all present
             if is_map:
                 t.insert_or_assign(dk, dev(vals + 9, k.value)); ref.insert_or_assign(keys, vals + 9)
                 assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
@@ -326,4 +333,96 @@ def test_l2_blocked_mutations_match_oracle(kind, native_lib):
                 assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
             t.close()
     finally:
-        native_lib.set_blocking(-1, 32)
+        native_lib.set_blocking(-1, 16)
+        native_lib.set_blocking_variant(2, 0, 1)
+
+
+def test_l2_blocked_large_batch_properties(native_lib):
+    """The blocked path at its intended size (auto mode picks it): 50 M uniform pairs with duplicates
+    at load factor 0.8 must give the same table as the direct path (size, per-key payloads)."""
+    n = 50_000_000
+    keys = torch.randint(1, n, (n,), device="cuda", dtype=torch.int64)
+    pairs = torch.stack([keys, keys * 7 + 3], dim=1).contiguous()
+    sizes, sums = [], []
+    try:
+        for mode in (0, 1):
+            native_lib.set_blocking(mode, 16)
+            t = cb.static_map(n=n, load_factor=0.8, probing="linear_probing", cg_size=1, _library=native_lib)
+            new = t.insert(pairs)
+            assert new == t.size()
+            assert torch.equal(t.find(keys), keys * 7 + 3)
+            assert not bool(t.contains(keys + n).any().item())
+            sizes.append(new)
+            t.close()
+            del t
+    finally:
+        native_lib.set_blocking(-1, 16)
+    assert sizes[0] == sizes[1] == int(torch.unique(keys).numel())
+    torch.cuda.empty_cache()
+
+
+def _run_device_checks(exe):
+    import subprocess
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith(("PASS", "FAIL"))]
+    return res.returncode, lines
+
+
+def test_device_checks_match_reference_headers():
+    """tests/device_checks.cu uses only the public cuco:: C++ API (bulk calls with fancy iterators,
+    device refs with every op tag, shared-memory tables, CTAD, heterogeneous lookup). The binary built
+    against include/ must pass every check, and print exactly what the build against the reference's
+    own headers prints."""
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    native = root / "tests" / "_build" / "device_checks_native"
+    assert native.exists(), "build it with __graft_entry__.build()"
+    rc, lines = _run_device_checks(native)
+    assert [ln for ln in lines if ln.startswith("FAIL")] == []
+    assert rc == 0 and len(lines) > 100
+    ref = root / "oracle" / "_ref" / "device_checks_ref"
+    if ref.exists():
+        ref_rc, ref_lines = _run_device_checks(ref)
+        assert ref_lines == lines
+        assert ref_rc == 0
+
+
+@pytest.mark.parametrize("kind", [_cabi.MAP_I64_LP1, _cabi.MAP_I32_LP4, _cabi.SET_I32_DH4])
+def test_host_buffer_entry_points_match_device_calls(kind, native_lib):
+    """cuco_b200_{insert,find,contains}_host: chunked + overlapped copies must give exactly what the
+    device-pointer calls give (several chunks: CUCO_B200_HOST_CHUNK defaults to 4 Mi elements)."""
+    k = cb.KINDS[kind]
+    is_map = k.value is not None
+    n = 9_000_001  # three chunks, the last one ragged
+    keys = torch.randint(1, n // 2, (n,), dtype=torch.int64).to(k.key)
+    vals = (keys.to(torch.int64) * 5 + 1).to(k.value) if is_map else None
+    queries = torch.cat([keys[: n // 2], keys[: n // 2] + n])
+    a = make(kind, native_lib, n=n, load_factor=0.5)
+    b = make(kind, native_lib, n=n, load_factor=0.5)
+    hk, hq = keys.pin_memory(), queries.pin_memory()
+    if is_map:
+        a.insert_host(hk, vals.pin_memory())
+        b.insert_async(keys.cuda(), vals.cuda())
+    else:
+        a.insert_host(hk)
+        b.insert_async(keys.cuda())
+    found = a.find_host(hq)
+    present = a.contains_host(hq)
+    torch.cuda.synchronize()
+    assert a.size() == b.size()
+    assert torch.equal(found, b.find(queries.cuda()).cpu())
+    assert torch.equal(present, b.contains(queries.cuda()).cpu())
+    a.close(); b.close()
+
+
+def test_host_buffer_insert_of_aos_pairs(native_lib):
+    n = 5_000_000
+    keys = torch.randperm(n, dtype=torch.int64)
+    pairs = torch.stack([keys, keys * 3], dim=1).contiguous().pin_memory()
+    t = make(_cabi.MAP_I64_LP1, native_lib, n=n, load_factor=0.8)
+    t.insert_host(pairs)
+    out = t.find_host(keys.pin_memory())
+    torch.cuda.synchronize()
+    assert t.size() == n
+    assert torch.equal(out, keys * 3)
+    t.close()
