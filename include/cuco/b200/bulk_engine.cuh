@@ -60,8 +60,9 @@ struct tuning_t {
   std::size_t region_bytes          = std::size_t{16} << 20;   ///< table slice kept L2-resident
   std::size_t blocked_min_table     = std::size_t{256} << 20;  ///< auto mode: table at least this big
   std::int64_t blocked_min_elements = std::int64_t{1} << 22;   ///< auto mode: batch at least this big
-  int blocked_keys_per_thread = 2;  ///< pass 2 of the blocked path: probes in flight per thread
-  bool blocked_cas_first      = false;  ///< pass 2 starts with the CAS (table slice is L2-resident)
+  int blocked_keys_per_thread = 4;  ///< pass 2 of the blocked path: probes in flight per thread
+  bool blocked_cas_first      = true;   ///< pass 2 starts with the CAS (table slice is L2-resident;
+                                        ///< measured 34.9 vs 30.6 Gops/s, profiles/r01_insert_probe_v4.jsonl)
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
   std::size_t l2_window_bytes = std::size_t{48} << 20;
 };
@@ -778,16 +779,18 @@ class table_engine {
 
     constexpr int chunk = EngineT::sector_chunk_slots;
     {
-      auto const kernel = route_kernel<block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
-      constexpr std::size_t smem = route_smem_bytes<block_size, value_type>();
+      auto const kernel =
+        route_kernel<route_block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
+      constexpr std::size_t smem = route_smem_bytes<route_block_size, value_type>();
       static bool const configured = [&] {
         return cudaFuncSetAttribute(
                  kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
       }();
       (void)configured;
-      auto const tiles = cuco::detail::int_div_ceil(n, index_type{block_size} * route_items_per_thread);
-      auto const grid  = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
-      kernel<<<grid, block_size, smem, stream.get()>>>(
+      auto const tiles =
+        cuco::detail::int_div_ceil(n, index_type{route_block_size} * route_items_per_thread);
+      auto const grid = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
+      kernel<<<grid, route_block_size, smem, stream.get()>>>(
         in, n, segments, counts, regions, segment_capacity, counter, engine, action);
     }
     {
@@ -820,7 +823,7 @@ class table_engine {
       };
       t.blocked_cas_first ? with_kpt(std::true_type{}) : with_kpt(std::false_type{});
 #else
-      run(std::integral_constant<int, 2>{}, std::false_type{});
+      run(std::integral_constant<int, 4>{}, std::true_type{});
 #endif
     }
   }

@@ -632,7 +632,8 @@ struct region_map {
   }
 };
 
-constexpr int route_items_per_thread = 16;
+constexpr int route_block_size       = 512;  ///< more warps per CTA hide the input-load latency
+constexpr int route_items_per_thread = 8;    ///< tile = 4096 elements
 constexpr int route_max_regions      = 1024;
 
 /// Dynamic shared memory of `route_kernel` for a slot type.
@@ -834,7 +835,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
 
   uninitialized<slot_type> val[KeysPerThread];
   cursor cur[KeysPerThread];
-  unsigned live = 0, claiming = 0, todo = 0;
+  unsigned live = 0, claiming = 0, todo = 0, rare = 0;
 
 #pragma unroll
   for (int j = 0; j < KeysPerThread; ++j) {
@@ -879,12 +880,15 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
                               val[j].value);
             state_of = 1;
           } else if (state == equal_result::AVAILABLE) {
-            cur[j].slot += i - begin_off;  // stays inside the sector, no wrap
+            if (i > begin_off) { engine.advance(cur[j], i - begin_off); }  // now at the free slot
             state_of = 2;
           }
         }
       }
-      if (state_of == 0) { todo |= 1u << j; }
+      if (state_of == 0) {
+        engine.advance(cur[j], valid);
+        todo |= 1u << j;
+      }
       if (state_of == 2) { claiming |= 1u << j; }
     }
   }
@@ -919,13 +923,98 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
     } else if (engine.classify_insert(Engine::key_of(val[j].value), Engine::key_of(seen[j])) ==
                equal_result::EQUAL) {
       action.on_present(engine, idx, address, seen[j], val[j].value);
+    } else if (engine.classify_insert(Engine::key_of(val[j].value), Engine::key_of(seen[j])) ==
+               equal_result::AVAILABLE) {
+      rare |= 1u << j;  // claimable, but not the canonical empty image (foreign payload bits)
     } else {
+      engine.advance(cur[j], 1);  // another key won this slot: carry on behind it
       todo |= 1u << j;
+    }
+  }
+
+  // Leftover keys (home sector full of other keys, or lost a race): warp-converged rounds. Every
+  // lane takes its lowest pending key and runs one probe step on it (sector load, scan, claim), so
+  // a round costs one pass through this body for the whole warp instead of one divergent walk
+  // per key.
+  while (__any_sync(0xffffffffu, todo != 0)) {
+    if (todo != 0) {
+      int const jj = __ffs(todo) - 1;
+      slot_type v  = val[0].value;
+      cursor c     = cur[0];
+#pragma unroll
+      for (int j = 1; j < KeysPerThread; ++j) {
+        if (j == jj) {
+          v = val[j].value;
+          c = cur[j];
+        }
+      }
+      index_type const idx = first_idx + index_type{jj} * BlockSize;
+      auto const& key      = Engine::key_of(v);
+      auto const raw       = engine.template load_chunk<ChunkSlots, policy>(c);
+      int const begin_off  = static_cast<int>(c.slot - Engine::template chunk_begin<ChunkSlots>(c));
+      int const valid      = engine.template chunk_valid<ChunkSlots>(c);
+      int outcome          = 0;  // 0: keep probing, 1: finished, 2: rare path
+      int consumed         = valid;
+#pragma unroll
+      for (int i = 0; i < ChunkSlots; ++i) {
+        if (outcome == 0 && consumed == valid && i >= begin_off && i < begin_off + valid) {
+          auto const slot  = chunk_slot<slot_type>(raw, i);
+          auto const state = engine.classify_insert(key, Engine::key_of(slot));
+          if (state == equal_result::EQUAL) {
+            action.on_present(engine, idx, table + (c.slot + (i - begin_off)), slot, v);
+            outcome = 1;
+          } else if (state == equal_result::AVAILABLE) {
+            consumed = i - begin_off;
+          }
+        }
+      }
+      if (outcome == 0) {
+        if (consumed > 0) { engine.advance(c, consumed); }
+        if (consumed < valid) {
+          // c.slot is the available slot: claim it
+          auto* const address = table + c.slot;
+          slot_type observed;
+          if constexpr (key_only_claim) {
+            key_type expected_key = Engine::key_of(empty_slot);
+            cuda::atomic_ref<key_type, Engine::thread_scope> key_ref{address->first};
+            key_ref.compare_exchange_strong(
+              expected_key, static_cast<key_type>(key), cuda::memory_order_relaxed);
+            observed       = empty_slot;
+            observed.first = expected_key;
+          } else {
+            observed = cas_slot<Engine::thread_scope>(address, empty_slot, v);
+          }
+          bool const won = key_only_claim
+                             ? same_bits(Engine::key_of(observed), Engine::key_of(empty_slot))
+                             : same_bits(observed, empty_slot);
+          if (won) {
+            action.on_new(engine, idx, address, v);
+            ++mine;
+            outcome = 1;
+          } else {
+            auto const state = engine.classify_insert(key, Engine::key_of(observed));
+            if (state == equal_result::EQUAL) {
+              action.on_present(engine, idx, address, observed, v);
+              outcome = 1;
+            } else if (state == equal_result::AVAILABLE) {
+              outcome = 2;
+            } else {
+              engine.advance(c, 1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KeysPerThread; ++j) {
+        if (j == jj) { cur[j] = c; }
+      }
+      if (outcome != 0) { todo &= ~(1u << jj); }
+      if (outcome == 2) { rare |= 1u << jj; }
     }
   }
 #pragma unroll
   for (int j = 0; j < KeysPerThread; ++j) {
-    if (todo & (1u << j)) {
+    if (rare & (1u << j)) {
       mine += mutate_slow_path<ChunkSlots, policy>(
         engine, val[j].value, first_idx + index_type{j} * BlockSize, action);
     }

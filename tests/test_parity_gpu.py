@@ -334,7 +334,7 @@ def test_l2_blocked_mutations_match_oracle(kind, variant, native_lib):
             t.close()
     finally:
         native_lib.set_blocking(-1, 16)
-        native_lib.set_blocking_variant(2, 0, 1)
+        native_lib.set_blocking_variant(4, 1, 1)
 
 
 def test_l2_blocked_large_batch_properties(native_lib):
