@@ -32,6 +32,9 @@ PLUS, MIN, MAX = 0, 1, 2
 
 _vp, _i64, _int, _dbl, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64
 _pi64 = C.POINTER(C.c_int64)
+_u32 = C.c_uint32
+_pu32 = C.POINTER(C.c_uint32)
+_pvp = C.POINTER(C.c_void_p)
 
 _PROTOTYPES = {
     "cuco_b200_build_info": (C.c_char_p, []),
@@ -59,6 +62,12 @@ _PROTOTYPES = {
     "cuco_b200_find_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "cuco_b200_contains_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "cuco_b200_insert_and_find_host": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cuco_b200_exchange_plan": (_int, [_vp, _i64, _int, _pu32, _pu32, _pu32]),
+    "cuco_b200_exchange_route": (_int, [_vp, _vp, _vp, _i64, _int, _u32, _u32, _u32, _int, _int, _u64,
+                                        _pvp, _pvp, _pvp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cuco_b200_exchange_mutate": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _int, _vp]),
+    "cuco_b200_exchange_lookup": (_int, [_vp, _vp, _vp, _pvp, _u32, _u32, _int, _int, _int, _vp]),
+    "cuco_b200_exchange_unpermute": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp]),
     "cuco_b200_set_tuning": (_int, [_int, _int, _int, _int, _int, _int, _int]),
     "cuco_b200_set_blocking": (_int, [_int, _int]),
     "cuco_b200_set_blocking_variant": (_int, [_int, _int, _int]),

@@ -673,6 +673,110 @@ int cuco_b200_insert_and_find_host(cuco_b200_table* t,
   });
 }
 
+int cuco_b200_exchange_plan(cuco_b200_table* t,
+                            int64_t n_max,
+                            int num_ranks,
+                            uint32_t* num_regions,
+                            uint32_t* segment_capacity,
+                            uint32_t* spill_capacity)
+{
+  return guarded([&] {
+    require(t && num_regions && segment_capacity && spill_capacity, "NULL argument");
+    auto const shape  = t->exchange_plan(n_max, num_ranks);
+    *num_regions      = shape.num_regions;
+    *segment_capacity = shape.segment_capacity;
+    *spill_capacity   = shape.spill_capacity;
+  });
+}
+
+int cuco_b200_exchange_route(cuco_b200_table* t,
+                             const void* keys,
+                             const void* values,
+                             int64_t n,
+                             int keys_only,
+                             uint32_t num_regions,
+                             uint32_t segment_capacity,
+                             uint32_t spill_capacity,
+                             int num_ranks,
+                             int my_rank,
+                             uint64_t salt,
+                             void* const* peer_segments,
+                             void* const* peer_counts,
+                             void* const* peer_flags,
+                             void* counts_local,
+                             void* position_local,
+                             void* spill,
+                             void* spill_index,
+                             void* spill_count,
+                             void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0) && peer_segments && peer_counts && peer_flags &&
+              counts_local && spill && spill_count,
+            "bad argument");
+    require(!keys_only || (position_local && spill_index), "lookups need the position buffers");
+    require(my_rank >= 0 && my_rank < num_ranks, "rank out of range");
+    t->exchange_route(keys, values, n, keys_only != 0,
+                      cuco_b200_table::exchange_shape{num_regions, segment_capacity, spill_capacity},
+                      num_ranks, my_rank, salt, peer_segments, peer_counts, peer_flags, counts_local,
+                      position_local, spill, spill_index, spill_count, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_mutate(cuco_b200_table* t,
+                              const void* segments,
+                              const void* counts_recv,
+                              uint32_t num_regions,
+                              uint32_t segment_capacity,
+                              int num_ranks,
+                              int reduce_op,
+                              void* stream)
+{
+  return guarded([&] {
+    require(t && segments && counts_recv, "NULL argument");
+    t->exchange_mutate(segments, counts_recv,
+                       cuco_b200_table::exchange_shape{num_regions, segment_capacity, 0}, num_ranks,
+                       reduce_op, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_lookup(cuco_b200_table* t,
+                              const void* segments,
+                              const void* counts_recv,
+                              void* const* peer_results,
+                              uint32_t num_regions,
+                              uint32_t segment_capacity,
+                              int num_ranks,
+                              int my_rank,
+                              int what,
+                              void* stream)
+{
+  return guarded([&] {
+    require(t && segments && counts_recv && peer_results, "NULL argument");
+    t->exchange_lookup(segments, counts_recv, peer_results,
+                       cuco_b200_table::exchange_shape{num_regions, segment_capacity, 0}, num_ranks,
+                       my_rank, what, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_unpermute(cuco_b200_table* t,
+                                 const void* results,
+                                 const void* position_local,
+                                 int64_t n,
+                                 void* out,
+                                 int what,
+                                 void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && ((results && position_local && out) || n == 0), "bad argument");
+    t->exchange_unpermute(results, position_local, n, out, what, stream);
+    check_launch();
+  });
+}
+
 int cuco_b200_set_tuning(int keys_per_thread,
                          int cas_first,
                          int sector_chunks,

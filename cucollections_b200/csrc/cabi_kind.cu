@@ -229,6 +229,125 @@ class table_impl final : public cuco_b200_table {
     }
   }
 
+  // ---- exchange path (no reference counterpart: our engine only) ----------------------------
+#if defined(CUCO_SHIM_REFERENCE)
+  exchange_shape exchange_plan(i64, int) override { throw unsupported(); }
+  void exchange_route(const void*, const void*, i64, bool, exchange_shape, int, int, std::uint64_t,
+                      void* const*, void* const*, void* const*, void*, void*, void*, void*, void*,
+                      void*) override
+  {
+    throw unsupported();
+  }
+  void exchange_mutate(const void*, const void*, exchange_shape, int, int, void*) override
+  {
+    throw unsupported();
+  }
+  void exchange_lookup(const void*, const void*, void* const*, exchange_shape, int, int, int, void*) override
+  {
+    throw unsupported();
+  }
+  void exchange_unpermute(const void*, const void*, i64, void*, int, void*) override { throw unsupported(); }
+  static std::invalid_argument unsupported()
+  {
+    return std::invalid_argument("the exchange path exists in the native build only");
+  }
+#else
+  using engine_t = std::decay_t<decltype(std::declval<container_t&>().b200_engine())>;
+  using plan_t   = typename engine_t::exchange_plan;
+  static plan_t to_plan(exchange_shape s) { return plan_t{s.num_regions, s.segment_capacity, s.spill_capacity}; }
+  static cuco::b200::exchange_peers to_peers(void* const* ptrs, int n)
+  {
+    cuco::b200::exchange_peers p{};
+    for (int i = 0; i < n; ++i) { p.base[i] = ptrs[i]; }
+    return p;
+  }
+
+  exchange_shape exchange_plan(i64 n_max, int num_ranks) override
+  {
+    auto const p = c_.b200_engine().plan_exchange(n_max, num_ranks);
+    return exchange_shape{p.num_regions, p.segment_capacity, p.spill_capacity};
+  }
+
+  void exchange_route(const void* keys, const void* values, i64 n, bool keys_only, exchange_shape shape,
+                      int num_ranks, int my_rank, std::uint64_t salt, void* const* peer_segments,
+                      void* const* peer_counts, void* const* peer_flags, void* counts_local,
+                      void* position_local, void* spill, void* spill_index, void* spill_count,
+                      void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto run          = [&](auto keys_only_tag, auto first) {
+      eng.template exchange_route_async<decltype(keys_only_tag)::value>(
+        first, n, to_plan(shape), num_ranks, my_rank, salt, to_peers(peer_segments, num_ranks),
+        to_peers(peer_counts, num_ranks), to_peers(peer_flags, num_ranks),
+        static_cast<unsigned int*>(counts_local), static_cast<std::uint32_t*>(position_local), spill,
+        static_cast<std::uint32_t*>(spill_index), static_cast<unsigned int*>(spill_count), handle, sref(s));
+    };
+    if (keys_only) {
+      run(std::true_type{}, static_cast<key_type const*>(keys));
+    } else {
+      with_input(keys, values, n, [&](auto first, auto) { run(std::false_type{}, first); });
+    }
+  }
+
+  void exchange_mutate(const void* segments, const void* counts_recv, exchange_shape shape, int num_ranks,
+                       int op, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto const* segs  = static_cast<slot_type const*>(segments);
+    auto const* cnts  = static_cast<unsigned int const*>(counts_recv);
+    if (op < 0) {
+      eng.exchange_mutate_async(segs, cnts, to_plan(shape), num_ranks, handle, cuco::b200::action_insert{}, sref(s));
+      return;
+    }
+    if constexpr (is_map) {
+      auto run = [&](auto functor) {
+        eng.exchange_mutate_async(segs, cnts, to_plan(shape), num_ranks, handle,
+                                  cuco::b200::action_apply<decltype(functor), false>{functor}, sref(s));
+      };
+      switch (op) {
+        case 0: run(cuco::reduce::plus{}); break;
+        case 1: run(cuco::reduce::min{}); break;
+        case 2: run(cuco::reduce::max{}); break;
+        default: throw std::invalid_argument("unknown reduce op");
+      }
+    } else {
+      throw std::invalid_argument("insert_or_apply is a static_map operation");
+    }
+  }
+
+  void exchange_lookup(const void* segments, const void* counts_recv, void* const* peer_results,
+                       exchange_shape shape, int num_ranks, int my_rank, int what, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto const* segs  = static_cast<key_type const*>(segments);
+    auto const* cnts  = static_cast<unsigned int const*>(counts_recv);
+    if (what == 0) {
+      eng.template exchange_lookup_async<payload_t>(segs, cnts, to_peers(peer_results, num_ranks), to_plan(shape),
+                                                    num_ranks, my_rank, handle, eng.make_find_emit(), sref(s));
+    } else {
+      eng.template exchange_lookup_async<std::uint8_t>(segs, cnts, to_peers(peer_results, num_ranks),
+                                                       to_plan(shape), num_ranks, my_rank, handle,
+                                                       cuco::b200::emit_present{}, sref(s));
+    }
+  }
+
+  void exchange_unpermute(const void* results, const void* position_local, i64 n, void* out, int what,
+                          void* s) override
+  {
+    auto const* pos = static_cast<std::uint32_t const*>(position_local);
+    if (what == 0) {
+      engine_t::exchange_unpermute_async(static_cast<payload_t const*>(results), pos, n,
+                                         static_cast<payload_t*>(out), sref(s));
+    } else {
+      engine_t::exchange_unpermute_async(static_cast<std::uint8_t const*>(results), pos, n,
+                                         static_cast<std::uint8_t*>(out), sref(s));
+    }
+  }
+#endif
+
  private:
   static cuda::stream_ref sref(void* s) { return cuda::stream_ref{static_cast<cudaStream_t>(s)}; }
 

@@ -29,6 +29,26 @@ struct cuco_b200_table {
   virtual void erase(const void* keys, std::int64_t n, void* stream) = 0;
   virtual std::int64_t retrieve_all(void* keys_out, void* values_out, void* stream) = 0;
   virtual void rehash(std::int64_t capacity, void* stream) = 0;
+
+  // ---- exchange path of hash-partitioned tables (native build only; see include/cuco_b200.h) ----
+  struct exchange_shape {
+    std::uint32_t num_regions, segment_capacity, spill_capacity;
+  };
+  virtual exchange_shape exchange_plan(std::int64_t n_max, int num_ranks) = 0;
+  virtual void exchange_route(const void* keys, const void* values, std::int64_t n, bool keys_only,
+                              exchange_shape shape, int num_ranks, int my_rank, std::uint64_t salt,
+                              void* const* peer_segments, void* const* peer_counts,
+                              void* const* peer_flags, void* counts_local, void* position_local,
+                              void* spill, void* spill_index, void* spill_count, void* stream) = 0;
+  /// op: -1 insert, 0/1/2 insert_or_apply plus/min/max
+  virtual void exchange_mutate(const void* segments, const void* counts_recv, exchange_shape shape,
+                               int num_ranks, int op, void* stream) = 0;
+  /// what: 0 find (payload / key), 1 contains (bytes)
+  virtual void exchange_lookup(const void* segments, const void* counts_recv,
+                               void* const* peer_results, exchange_shape shape, int num_ranks,
+                               int my_rank, int what, void* stream) = 0;
+  virtual void exchange_unpermute(const void* results, const void* position_local, std::int64_t n,
+                                  void* out, int what, void* stream) = 0;
 };
 
 // Factory signature every cabi_kind.cu instance exports (C++ linkage, hidden from the C ABI).

@@ -25,6 +25,7 @@ stand-in from tests/ to exercise the plumbing without a GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import statistics
 
 import torch
@@ -82,11 +83,153 @@ class GpuBackend:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
 
+class FusedExchange:
+    """Fused routing over peer memory (cuco_b200_exchange_*, include/cuco_b200.h): one kernel groups
+    the batch by (owner, L2 region of the owner's shard) and stores it into the owners' buffers over
+    NVLink; the owner probes region by region; lookup results are stored back the same way. Buffers
+    live in torch symmetric memory so every rank can address every peer's copy. Native build only."""
+
+    def __init__(self, table, n_max, group, device, salt):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.table, self.lib, self.device, self.salt = table, table._lib, torch.device(device), salt
+        self.group = group
+        self.P, self.me = dist.get_world_size(group), dist.get_rank(group)
+        r, cap, spill = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.check(self.lib.exchange_plan(table._handle, int(n_max), self.P, C.byref(r), C.byref(cap),
+                                              C.byref(spill)))
+        self.R, self.cap, self.spill_cap, self.n_max = r.value, cap.value, spill.value, int(n_max)
+        k = table.kind
+        self.key_bytes = k.key.itemsize
+        self.slot_bytes = self.key_bytes + (k.value.itemsize if k.value is not None else 0)
+        self.result_dtype = k.value if k.value is not None else k.key
+        seg_elems = self.P * self.R * self.cap
+
+        def pad(x):
+            return (x + 255) // 256 * 256
+
+        self.off_segments = 0
+        self.off_counts = pad(seg_elems * self.slot_bytes)
+        self.off_flags = self.off_counts + pad(self.R * self.P * 4)
+        self.off_results = self.off_flags + pad(self.P * 4)
+        total = self.off_results + pad(seg_elems * 8)
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        vp = C.c_void_p * self.P
+        self.peer_segments = vp(*[p + self.off_segments for p in ptrs])
+        self.peer_counts = vp(*[p + self.off_counts for p in ptrs])
+        self.peer_flags = vp(*[p + self.off_flags for p in ptrs])
+        self.peer_results = vp(*[p + self.off_results for p in ptrs])
+        base = self.buf.data_ptr()
+        self.my_segments = C.c_void_p(base + self.off_segments)
+        self.my_counts = C.c_void_p(base + self.off_counts)
+        self.my_results = C.c_void_p(base + self.off_results)
+        self.flags = self.buf[self.off_flags:self.off_flags + self.P * 4].view(torch.int32)
+        self.flags.zero_()
+        self.counts_local = torch.zeros(self.P * self.R, dtype=torch.int32, device=self.device)
+        self.position_local = torch.empty(max(1, self.n_max), dtype=torch.int32, device=self.device)
+        self.spill = torch.empty(self.spill_cap * self.slot_bytes, dtype=torch.uint8, device=self.device)
+        self.spill_index = torch.empty(self.spill_cap, dtype=torch.int32, device=self.device)
+        self.spill_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.flags_host = torch.zeros(self.P, dtype=torch.int32).pin_memory()
+        # CUCO_B200_EXCHANGE_TRACE=1: CUDA events around every stage, summarised by trace_summary()
+        self.trace = [] if os.environ.get("CUCO_B200_EXCHANGE_TRACE") else None
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)
+
+    def _mark(self, label):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.device))
+            self.trace.append((label, e))
+
+    def trace_summary(self):
+        """Median milliseconds per stage label (time since the previous mark) over all traced calls
+        (mutations and lookups share the routing labels)."""
+        if not self.trace:
+            return {}
+        torch.cuda.synchronize(self.device)
+        samples = {}
+        for (_, a), (label, b) in zip(self.trace, self.trace[1:]):
+            if label != "begin":
+                samples.setdefault(label, []).append(a.elapsed_time(b))
+        return {k: round(statistics.median(v), 4) for k, v in samples.items()}
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def _route(self, elems, values, n, keys_only):
+        if n > self.n_max:
+            raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
+        self._mark("begin")
+        self._barrier()  # every owner has consumed the previous exchange
+        self._mark("barrier (previous exchange consumed)")
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_route(
+                self.table._handle, _vp(elems), _vp(values), n, int(keys_only), self.R, self.cap, self.spill_cap,
+                self.P, self.me, self.salt, self.peer_segments, self.peer_counts, self.peer_flags,
+                _vp(self.counts_local), _vp(self.position_local), _vp(self.spill), _vp(self.spill_index),
+                _vp(self.spill_count), self._stream()))
+        self._mark("route + publish")
+        self._barrier()  # segments, counts and flags of every source have landed
+        self._mark("barrier (segments landed)")
+
+    def _spilled(self):
+        """(total spilled over all ranks, spilled here): one 4*P byte read-back per bulk call."""
+        self.flags_host.copy_(self.flags, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        mine = int(self.flags_host[self.me].item())
+        if mine > self.spill_cap:
+            raise RuntimeError("batch too skewed for the exchange buffers: spill list overflowed")
+        return int(self.flags_host.sum().item()), mine
+
+    def mutate(self, pairs, reduce_op=-1):
+        """Routes and applies a batch of [n, 2] pairs; returns this rank's spilled pairs (or None)."""
+        n = pairs.shape[0]
+        self._route(pairs, None, n, False)
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_mutate(self.table._handle, self.my_segments, self.my_counts,
+                                                    self.R, self.cap, self.P, reduce_op, self._stream()))
+        self._mark("probe received segments")
+        total, mine = self._spilled()
+        if total == 0:
+            return None
+        return self.spill[: mine * self.slot_bytes].view(pairs.dtype).view(mine, 2).clone()
+
+    def lookup(self, keys, out, what):
+        """what: 0 find, 1 contains. Returns (spilled keys, their source indices) or None."""
+        n = keys.shape[0]
+        self._route(keys, None, n, True)
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_lookup(self.table._handle, self.my_segments, self.my_counts,
+                                                    self.peer_results, self.R, self.cap, self.P, self.me, what,
+                                                    self._stream()))
+        self._mark("lookup received segments")
+        self._barrier()  # every owner has stored this rank's results
+        self._mark("barrier (results landed)")
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_unpermute(self.table._handle, self.my_results,
+                                                       _vp(self.position_local), n, _vp(out), what,
+                                                       self._stream()))
+        self._mark("unpermute")
+        total, mine = self._spilled()
+        if total == 0:
+            return None
+        return (self.spill[: mine * self.key_bytes].view(keys.dtype).clone(),
+                self.spill_index[:mine].to(torch.int64))
+
+
 class partitioned_static_map:
     """static_map<int64,int64> sharded over the ranks of `group` by owner(key)."""
 
     def __init__(self, n_total, load_factor=0.5, *, backend, group=None, salt=DEFAULT_SALT,
-                 headroom=1.03, **table_kw):
+                 headroom=1.03, fused_batch=None, **table_kw):
+        """`fused_batch`: largest batch (elements per rank and call) the fused exchange path is sized
+        for; None keeps the all_to_all routing (also the fallback for spilled elements)."""
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -96,6 +239,9 @@ class partitioned_static_map:
         # every shard at or below the requested load factor
         n_local = int(-(-n_total // self.world) * headroom) + 1
         self.table = backend.make_table(n_local, load_factor, **table_kw)
+        self.fused = None
+        if fused_batch:
+            self.fused = FusedExchange(self.table, fused_batch, group, backend.device, salt)
 
     # ---- exchange helpers ------------------------------------------------------------------------
     def _exchange_counts(self, send_counts):
@@ -126,32 +272,54 @@ class partitioned_static_map:
     # ---- bulk API --------------------------------------------------------------------------------
     def insert_async(self, pairs):
         """pairs: [n, 2] int64 (key, value) on this rank. Stream-ordered on every rank."""
+        if self.fused is not None:
+            pairs = self.fused.mutate(pairs)
+            if pairs is None:
+                return
         received, *_ = self._route(pairs, True, False)
         self.table.insert_async(received)
 
     def insert(self, pairs) -> int:
-        """Returns the number of new keys over all ranks."""
+        """Returns the number of new keys over all ranks (collective routing: it needs the count)."""
         received, *_ = self._route(pairs, True, False)
         new = torch.tensor([self.table.insert(received)], dtype=torch.int64)
         return self._allreduce_sum(new)
 
     def insert_or_apply(self, pairs, op="plus", init=None):
+        if self.fused is not None and init is None:
+            pairs = self.fused.mutate(pairs, {"plus": _cabi.PLUS, "min": _cabi.MIN, "max": _cabi.MAX}[op])
+            if pairs is None:
+                return
         received, *_ = self._route(pairs, True, False)
         self.table.insert_or_apply(received, op=op, init=init)
 
-    def find(self, keys, out=None):
+    def _lookup(self, keys, out, what):
+        """what: 0 find, 1 contains (uint8 results)."""
+        if self.fused is not None:
+            spilled = self.fused.lookup(keys, out, what)
+            if spilled is None:
+                return out
+            keys, where = spilled  # finish the spilled keys through the collective path
+            part = self.backend.empty((keys.shape[0],), out.dtype)
+            self._lookup_collective(keys, part, what)
+            out[where] = part
+            return out
+        return self._lookup_collective(keys, out, what)
+
+    def _lookup_collective(self, keys, out, what):
         received, send_counts, recv_counts, index = self._route(keys, False, True)
-        results = self.table.find(received)
-        if out is None:
-            out = self.backend.empty((keys.shape[0],), results.dtype)
+        results = self.table.find(received) if what == 0 else self.table.contains(received).view(torch.uint8)
         return self._return(results, send_counts, recv_counts, index, out)
 
+    def find(self, keys, out=None):
+        if out is None:
+            out = self.backend.empty((keys.shape[0],), self.table._payload_dtype())
+        return self._lookup(keys, out, 0)
+
     def contains(self, keys, out=None):
-        received, send_counts, recv_counts, index = self._route(keys, False, True)
-        results = self.table.contains(received).view(torch.uint8)
         if out is None:
             out = self.backend.empty((keys.shape[0],), torch.uint8)
-        return self._return(results, send_counts, recv_counts, index, out).view(torch.bool)
+        return self._lookup(keys, out.view(torch.uint8), 1).view(torch.bool)
 
     def clear_async(self):
         self.table.clear_async()
@@ -175,6 +343,16 @@ class partitioned_static_map:
 # ==================================================================================================
 # benchmark entry (bench.py --gpus N under torchrun)
 # ==================================================================================================
+def _hbm_peak():
+    import json
+    from pathlib import Path
+    p = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def bench(args, lib, impl):
     import json  # noqa: F401
     import os
@@ -195,7 +373,9 @@ def bench(args, lib, impl):
     keys = kg.uniform(n, 1, torch.int64, dev, seed=42 + rank) + rank * n
     pairs = torch.stack([keys, keys], dim=1).contiguous()
     out = torch.empty(n, dtype=torch.int64, device=dev)
+    routing = os.environ.get("CUCO_B200_ROUTING", "fused" if impl == "native" else "nccl")
     table = partitioned_static_map(n * world, 0.5, backend=GpuBackend(dev, lib),
+                                   fused_batch=n if routing == "fused" else None,
                                    probing="linear_probing", cg_size=1)
 
     def step():
@@ -267,7 +447,9 @@ def bench(args, lib, impl):
         "data": "synthetic",
         "impl": impl,
         "config": {"workload": f"hash-partitioned static_map<int64,int64>, {n} uniform pairs per GPU "
-                               f"insert + find, LF 0.5, linear_probing<1>, {world} GPUs, NCCL all-to-all routing",
+                               f"insert + find, LF 0.5, linear_probing<1>, {world} GPUs, "
+                               + ("fused P2P routing over NVLink (one partition kernel stores into the owners' memory)"
+                                  if routing == "fused" else "NCCL all-to-all routing"),
                    "n_per_gpu": n, "total_size": total_size,
                    "timing": "CUDA events per rank around partition + all-to-all + local kernels, "
                              "max over ranks; clear outside; working sets larger than L2"},
@@ -275,19 +457,27 @@ def bench(args, lib, impl):
         "find_gops": n * world / (fnd * 1e-3) / 1e9,
         "insert_ms": ins,
         "find_ms": fnd,
-        "roofline": {"bound": "nvlink", "achieved": 16.0 * n * (world - 1) / world / (ins * 1e-3) / 1e9,
-                     "peak": 770.0, "unit": "GB/s",
-                     "frac": 16.0 * n * (world - 1) / world / (ins * 1e-3) / 1e9 / 770.0,
-                     "traffic": None,
-                     "note": "insert is bounded by the per-GPU all-to-all egress (16 B per pair leaving "
-                             "the rank) against the measured 770 GB/s peer copy, not by HBM"},
+        # per GPU the insert moves the single-GPU algorithmic bytes (80 B/op) through HBM and
+        # 16 B * (P-1)/P per pair through NVLink; report the HBM view (same definition as N=1) and
+        # the NVLink egress next to it
+        "roofline": {"bound": "hbm", "kernel": "insert (exchange_route_kernel + blocked_mutate_kernel)"
+                     if routing == "fused" else "insert (partition + all_to_all + local insert)",
+                     "achieved": 80.0 * n / (ins * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s",
+                     "frac": 80.0 * n / (ins * 1e-3) / 1e9 / _hbm_peak(), "traffic": None,
+                     "per_gpu": True,
+                     "nvlink_egress_gbs": 16.0 * n * (world - 1) / world / (ins * 1e-3) / 1e9,
+                     "nvlink_peak_gbs": 770.0},
         "e2e": {"value": ops / (e2e_ms * 1e-3) / 1e9, "unit": "Gops/s",
                 "h2d_bytes_per_step": int(n * 24 * world), "d2h_bytes_per_step": int(n * 8 * world),
                 "ms_per_step": e2e_ms},
-        # per step and rank: 2 partition passes x (count + scatter) + insert + find + unpermute
-        "gpu_launches": 7 * args.steps * world,
+        # our kernels per step and rank. fused: insert = route + publish + probe, find = route +
+        # publish + lookup + unpermute; all_to_all routing: 2 x (count + scatter) + insert (route +
+        # probe when blocked) + find + scatter_by_index
+        "gpu_launches": (7 if routing == "fused" else 8) * args.steps * world,
         "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled in multi-GPU mode"]},
     }
+    if table.fused is not None and table.fused.trace is not None and rank == 0:
+        result["exchange_trace_ms"] = table.fused.trace_summary()
     table.close()
     dist.barrier()
     return result

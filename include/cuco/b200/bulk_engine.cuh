@@ -64,6 +64,7 @@ struct tuning_t {
   bool blocked_cas_first      = true;   ///< pass 2 starts with the CAS (table slice is L2-resident;
                                         ///< measured 34.9 vs 30.6 Gops/s, profiles/r01_insert_probe_v4.jsonl)
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
+  int exchange_lookup_keys_per_thread = 2;  ///< owner side of routed lookups (1, 2 or 4)
   std::size_t l2_window_bytes = std::size_t{48} << 20;
 };
 
@@ -82,6 +83,9 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_KPT")) { t.blocked_keys_per_thread = std::atoi(s); }
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_CAS_FIRST")) { t.blocked_cas_first = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_PREFETCH")) { t.blocked_prefetch = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_EXCHANGE_LOOKUP_KPT")) {
+    t.exchange_lookup_keys_per_thread = std::atoi(s);
+  }
   if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
     t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
   }
@@ -809,7 +813,8 @@ class table_engine {
           segment_capacity,
           region_slots,
           table_bytes,
-          t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u};
+          t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
+          1u};
         kernel<<<dim3{tiles_per_segment, num_regions}, block_size, 0, stream.get()>>>(
           segments, layout, counter, engine, action);
       };
@@ -828,6 +833,202 @@ class table_engine {
     }
   }
 
+  // ------------------------------------------------------------------------------------------
+  // exchange path of hash-partitioned tables (see bulk_kernels.cuh, "Exchange path")
+  // ------------------------------------------------------------------------------------------
+ public:
+  /// Buffer geometry for batches of at most `n_max` elements per rank over `num_ranks` shards.
+  struct exchange_plan {
+    std::uint32_t num_regions;       ///< R: L2 regions per shard (num_ranks * R <= 1024)
+    std::uint32_t segment_capacity;  ///< elements per (owner, region, source) segment
+    std::uint32_t spill_capacity;    ///< elements of the local spill list
+  };
+
+  [[nodiscard]] exchange_plan plan_exchange(cuco::detail::index_type n_max, int num_ranks) const
+  {
+    CUCO_EXPECTS(num_ranks >= 1 && num_ranks <= exchange_max_ranks, "unsupported number of ranks");
+    CUCO_EXPECTS(n_max >= 0 && n_max < (cuco::detail::index_type{1} << 32),
+                 "exchange batches are limited to 2^32 - 1 elements per rank");
+    auto const& t          = tuning();
+    auto const table_bytes = static_cast<std::uint64_t>(storage_.capacity()) * sizeof(value_type);
+    auto const max_regions = static_cast<std::uint64_t>(route_max_regions / num_ranks);
+    auto const regions     = std::max<std::uint64_t>(
+      1, std::min<std::uint64_t>(max_regions, (table_bytes + t.region_bytes - 1) / t.region_bytes));
+    auto const segments = regions * static_cast<std::uint64_t>(num_ranks);
+    auto const mean     = (static_cast<std::uint64_t>(n_max) + segments - 1) / segments;
+    return exchange_plan{static_cast<std::uint32_t>(regions),
+                         static_cast<std::uint32_t>(mean + mean / 16 + 1024),
+                         static_cast<std::uint32_t>(
+                           std::max<std::uint64_t>(65536, static_cast<std::uint64_t>(n_max) / 8))};
+  }
+
+  /// Source side: groups [first, first + n) by (owner, region) and stores it into the owners'
+  /// segment buffers; then publishes the fill counts and this rank's spill count to the peers.
+  /// The caller zeroes nothing: `counts_local` and `spill_count` are reset here, on `stream`.
+  template <bool KeysOnly, typename InputIt, typename Ref>
+  void exchange_route_async(InputIt first,
+                            cuco::detail::index_type n,
+                            exchange_plan plan,
+                            int num_ranks,
+                            int my_rank,
+                            std::uint64_t salt,
+                            exchange_peers segments,
+                            exchange_peers counts_recv,
+                            exchange_peers spill_flags,
+                            unsigned int* counts_local,
+                            std::uint32_t* position_local,
+                            void* spill,
+                            std::uint32_t* spill_index,
+                            unsigned int* spill_count,
+                            Ref ref,
+                            cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    auto in           = unwrap(first);
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    using elem_type   = std::conditional_t<KeysOnly, key_type, value_type>;
+    auto const capacity = static_cast<std::uint64_t>(storage_.capacity());
+    exchange_geometry const geometry{static_cast<std::uint32_t>(num_ranks),
+                                     static_cast<std::uint32_t>(my_rank),
+                                     plan.num_regions,
+                                     plan.segment_capacity,
+                                     salt};
+    auto const buckets = static_cast<std::size_t>(num_ranks) * plan.num_regions;
+    CUCO_CUDA_TRY(cudaMemsetAsync(counts_local, 0, buckets * sizeof(unsigned int), stream.get()));
+    CUCO_CUDA_TRY(cudaMemsetAsync(spill_count, 0, sizeof(unsigned int), stream.get()));
+    if (n > 0) {
+      unsigned __int128 const scaled = (static_cast<unsigned __int128>(plan.num_regions) << 64) / capacity;
+      region_map const regions{static_cast<std::uint64_t>(scaled) + 1, plan.num_regions};
+      auto const kernel = exchange_route_kernel<route_block_size, KeysOnly, decltype(in), engine_t>;
+      constexpr std::size_t smem = exchange_smem_bytes<route_block_size, elem_type, KeysOnly>();
+      static bool const configured = [&] {
+        return cudaFuncSetAttribute(
+                 kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+      }();
+      (void)configured;
+      auto const tiles = cuco::detail::int_div_ceil(n, index_type{route_block_size} * route_items_per_thread);
+      auto const grid  = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
+      kernel<<<grid, route_block_size, smem, stream.get()>>>(in,
+                                                             n,
+                                                             segments,
+                                                             counts_local,
+                                                             position_local,
+                                                             spill,
+                                                             spill_index,
+                                                             spill_count,
+                                                             plan.spill_capacity,
+                                                             regions,
+                                                             geometry,
+                                                             engine);
+    }
+    auto const publish_grid = static_cast<unsigned>((buckets + 255) / 256);
+    exchange_publish_kernel<<<publish_grid, 256, 0, stream.get()>>>(
+      counts_local, spill_count, counts_recv, spill_flags, geometry);
+  }
+
+  /// Owner side of a routed mutation: probes the received segments region by region.
+  template <typename Ref, typename Action>
+  void exchange_mutate_async(value_type const* segments,
+                             unsigned int const* counts_recv,
+                             exchange_plan plan,
+                             int num_ranks,
+                             Ref ref,
+                             Action action,
+                             cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    if constexpr (!(engine_t::single_cas && engine_t::pow2_slot)) {
+      CUCO_FAIL("the exchange path needs slots that one CAS can claim (4, 8 or packed 16 bytes)");
+    } else {
+    CUCO_EXPECTS(this->fast_path_ok(true), "the exchange path needs container-owned storage without tombstones");
+    auto const& t           = tuning();
+    auto const capacity     = static_cast<std::uint64_t>(storage_.capacity());
+    constexpr int chunk     = engine_t::sector_chunk_slots;
+    constexpr int kpt       = 4;
+    auto const kernel       = blocked_mutate_kernel<block_size, kpt, chunk, true, false, size_type, engine_t, Action>;
+    auto const tiles_per_segment = static_cast<unsigned>(
+      cuco::detail::int_div_ceil(index_type{plan.segment_capacity}, index_type{block_size} * kpt));
+    auto const region_slots = (capacity + plan.num_regions - 1) / plan.num_regions;
+    auto const region_bytes = region_slots * sizeof(value_type);
+    auto const shares       = static_cast<std::uint64_t>(tiles_per_segment) * num_ranks;
+    auto const share        = (region_bytes + shares - 1) / shares;
+    blocked_layout const layout{counts_recv,
+                                plan.segment_capacity,
+                                region_slots,
+                                capacity * sizeof(value_type),
+                                t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
+                                static_cast<std::uint32_t>(num_ranks)};
+    kernel<<<dim3{tiles_per_segment, plan.num_regions * static_cast<unsigned>(num_ranks)},
+             block_size,
+             0,
+             stream.get()>>>(segments, layout, static_cast<size_type*>(nullptr), engine, action);
+    }
+  }
+
+  /// Owner side of a routed lookup: results go straight into the sources' result buffers.
+  template <typename Result, typename Ref, typename Emit>
+  void exchange_lookup_async(key_type const* segments,
+                             unsigned int const* counts_recv,
+                             exchange_peers results,
+                             exchange_plan plan,
+                             int num_ranks,
+                             int my_rank,
+                             Ref ref,
+                             Emit emit,
+                             cuda::stream_ref stream) const
+  {
+    using cuco::detail::index_type;
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    CUCO_EXPECTS(this->fast_path_ok(false), "the exchange path needs container-owned storage");
+    constexpr int chunk = engine_t::sector_chunk_slots;
+    exchange_geometry const geometry{static_cast<std::uint32_t>(num_ranks),
+                                     static_cast<std::uint32_t>(my_rank),
+                                     plan.num_regions,
+                                     plan.segment_capacity,
+                                     0};
+    auto run = [&](auto kpt_tag) {
+      constexpr int kpt            = decltype(kpt_tag)::value;
+      auto const tiles_per_segment = static_cast<unsigned>(
+        cuco::detail::int_div_ceil(index_type{plan.segment_capacity}, index_type{block_size} * kpt));
+      exchange_lookup_kernel<block_size, kpt, chunk, Result>
+        <<<dim3{tiles_per_segment, plan.num_regions * static_cast<unsigned>(num_ranks)},
+           block_size,
+           0,
+           stream.get()>>>(segments, counts_recv, results, geometry, engine, emit);
+    };
+    switch (tuning().exchange_lookup_keys_per_thread) {
+      case 1: run(std::integral_constant<int, 1>{}); break;
+      case 4: run(std::integral_constant<int, 4>{}); break;
+      default: run(std::integral_constant<int, 2>{}); break;
+    }
+  }
+
+  /// Source side of a routed lookup: out[i] = result of key i, for the n keys this rank routed.
+  template <typename Result, typename OutputIt>
+  static void exchange_unpermute_async(Result const* results,
+                                       std::uint32_t const* position_local,
+                                       cuco::detail::index_type n,
+                                       OutputIt out,
+                                       cuda::stream_ref stream)
+  {
+    if (n == 0) { return; }
+    auto const blocks = cuco::detail::int_div_ceil(n, cuco::detail::index_type{256} * 4);
+    exchange_unpermute_kernel<<<static_cast<unsigned>(std::min<cuco::detail::index_type>(blocks, 0x7fffffff)),
+                                256,
+                                0,
+                                stream.get()>>>(results, position_local, n, unwrap(out));
+  }
+
+  [[nodiscard]] auto make_find_emit() const noexcept
+  {
+    return emit_found<engine_type>{empty_slot_sentinel_};
+  }
+
+ private:
   /// Picks the (keys per thread, chunk width) instantiation.
   template <typename EngineT, bool Mutating = false, typename Run>
   static void dispatch_variant(Run&& run)

@@ -773,6 +773,7 @@ struct blocked_layout {
   std::uint64_t region_slots;       ///< ceil(capacity / num_regions): slots per region
   std::uint64_t table_bytes;        ///< end of the slot array (prefetch clamp)
   std::uint32_t prefetch_bytes;     ///< per-CTA share of the next region (multiple of 128), 0 = off
+  std::uint32_t sources;            ///< segments per region (1; number of ranks for exchanged batches)
 };
 
 template <int BlockSize,
@@ -791,12 +792,17 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
   Action action)
 {
   constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
-  std::uint32_t const region = blockIdx.y;
+  // segment = region * sources + source: CTAs are dispatched region by region
+  std::uint32_t const segment     = blockIdx.y;
+  std::uint32_t const region      = segment / layout.sources;
+  std::uint32_t const num_regions = gridDim.y / layout.sources;
 
-  if (layout.prefetch_bytes != 0 && threadIdx.x == 0 && region + 1 < gridDim.y) {
+  if (layout.prefetch_bytes != 0 && threadIdx.x == 0 && region + 1 < num_regions) {
     // stream this CTA's share of the next region's slots into L2 while this region is probed
+    std::uint64_t const share_index =
+      std::uint64_t{segment - region * layout.sources} * gridDim.x + blockIdx.x;
     std::uint64_t const begin = (std::uint64_t{region} + 1) * layout.region_slots * Engine::slot_bytes +
-                                std::uint64_t{blockIdx.x} * layout.prefetch_bytes;
+                                share_index * layout.prefetch_bytes;
     std::uint64_t const limit = (std::uint64_t{region} + 2) * layout.region_slots * Engine::slot_bytes;
     std::uint64_t end = begin + layout.prefetch_bytes;
     if (end > limit) { end = limit; }
@@ -810,7 +816,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
     }
   }
 
-  auto const stored = layout.counts[region];
+  auto const stored = layout.counts[segment];
   index_type const count =
     stored < layout.segment_capacity ? index_type{stored} : index_type{layout.segment_capacity};
   index_type const tile_base = index_type{blockIdx.x} * tile;
@@ -827,8 +833,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
   constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
   constexpr auto policy         = load_policy::streaming;
 
-  index_type const first_idx = index_type{region} * layout.segment_capacity + tile_base + threadIdx.x;
-  index_type const limit     = index_type{region} * layout.segment_capacity + count;
+  index_type const first_idx = index_type{segment} * layout.segment_capacity + tile_base + threadIdx.x;
+  index_type const limit     = index_type{segment} * layout.segment_capacity + count;
   auto* const table          = engine.slots();
   auto const empty_slot      = engine.empty_slot_sentinel();
   unsigned long long mine    = 0;
@@ -1020,6 +1026,411 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
     }
   }
   if constexpr (Counted) { accumulate_count(num_new, mine); }
+}
+
+// =================================================================================================
+// Exchange path of hash-partitioned tables: ONE routing kernel groups a rank's batch by owner rank
+// AND by L2 region of the owner's table and stores it straight into the owners' memory
+// =================================================================================================
+//
+// No reference counterpart (cuCollections is single-GPU). Every rank holds one shard
+// with identical geometry, so a sender can compute the region an element will land in on its owner.
+// `exchange_route_kernel` is `route_kernel` with the combined bucket (owner, region): the staged runs
+// are written with plain stores through peer pointers (NVLink 5 / NVSwitch P2P; the run granularity
+// is what keeps those stores line-sized), so routing, the all-to-all and the L2 grouping of the
+// owner's pass 2 are the same kernel. Layouts (cap = segment capacity in elements):
+//   on the owner `o`:   segment g = region * P + source      at element offset g * cap
+//   on the source `s`:  segment l = owner * R + region        (counters, source indices, results)
+// A source is the only writer of its segments, so their fill counts are local atomics and are
+// published to the owners by `exchange_publish_kernel` before the cross-rank barrier. Elements
+// that do not fit their segment (heavily skewed batches) go to a local spill list that the host
+// side finishes through the collective fallback.
+
+constexpr int exchange_max_ranks = 16;
+
+/// Peer base pointers of one exchange buffer (index = rank).
+struct exchange_peers {
+  void* base[exchange_max_ranks];
+};
+
+/// Owner of a key: high bits of a mix that shares nothing with the in-table hash.
+__host__ __device__ inline std::uint32_t exchange_owner(std::uint64_t key_bits,
+                                                        std::uint64_t salt,
+                                                        std::uint32_t num_ranks) noexcept
+{
+  std::uint64_t x = key_bits ^ salt;
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+#if defined(__CUDA_ARCH__)
+  return static_cast<std::uint32_t>(__umul64hi(x, std::uint64_t{num_ranks}));
+#else
+  return static_cast<std::uint32_t>((static_cast<unsigned __int128>(x) * num_ranks) >> 64);
+#endif
+}
+
+struct exchange_geometry {
+  std::uint32_t num_ranks;         ///< P
+  std::uint32_t my_rank;
+  std::uint32_t num_regions;       ///< R (P * R <= route_max_regions)
+  std::uint32_t segment_capacity;  ///< cap
+  std::uint64_t salt;
+};
+
+template <typename Key>
+__device__ __forceinline__ std::uint64_t exchange_key_bits(Key const& key) noexcept
+{
+  if constexpr (sizeof(Key) == 8) {
+    std::uint64_t bits;
+    memcpy(&bits, &key, 8);
+    return bits;
+  } else {
+    static_assert(sizeof(Key) == 4);
+    std::int32_t bits;
+    memcpy(&bits, &key, 4);
+    return static_cast<std::uint64_t>(static_cast<std::int64_t>(bits));  // sign-extended like int64(key)
+  }
+}
+
+/// Dynamic shared memory of `exchange_route_kernel`.
+template <int BlockSize, typename Elem, bool WithIndex>
+constexpr std::size_t exchange_smem_bytes() noexcept
+{
+  return std::size_t{BlockSize} * route_items_per_thread *
+         (sizeof(Elem) + sizeof(std::uint16_t) + (WithIndex ? sizeof(std::uint32_t) : 0));
+}
+
+/// KeysOnly = false: elements are slot images (mutations); true: elements are keys (lookups), and
+/// the position each key's result will come back to is recorded in `position_local`.
+template <int BlockSize, bool KeysOnly, typename InputIt, typename Engine>
+CUCO_KERNEL __launch_bounds__(BlockSize, 2) void exchange_route_kernel(
+  InputIt first,
+  index_type n,
+  exchange_peers peers,            ///< owners' segment buffers
+  unsigned int* counts_local,      ///< [P * R] fill counts of this rank's segments
+  std::uint32_t* position_local,   ///< [n] source-side position of every routed key (KeysOnly);
+                                   ///< 0xffffffff for keys that went to the spill list
+  void* spill,                     ///< [spill_capacity] elements that did not fit
+  std::uint32_t* spill_index,      ///< their source indices (KeysOnly)
+  unsigned int* spill_count,
+  std::uint32_t spill_capacity,
+  region_map regions,
+  exchange_geometry geometry,
+  Engine engine)
+{
+  using slot_type = typename Engine::value_type;
+  using key_type  = typename Engine::key_type;
+  using elem_type = cuda::std::conditional_t<KeysOnly, key_type, slot_type>;
+  constexpr int items       = route_items_per_thread;
+  constexpr index_type tile = index_type{BlockSize} * items;
+  constexpr int buckets_per_thread = (route_max_regions + BlockSize - 1) / BlockSize;
+
+  extern __shared__ __align__(16) unsigned char route_dynamic_smem[];
+  auto* const stage  = reinterpret_cast<elem_type*>(route_dynamic_smem);   // [tile]
+  auto* const origin = reinterpret_cast<std::uint32_t*>(stage + tile);     // [tile] (KeysOnly)
+  auto* const bucket_of =
+    reinterpret_cast<std::uint16_t*>(origin + (KeysOnly ? tile : 0));       // [tile]
+  __shared__ unsigned int tile_hist[route_max_regions];
+  __shared__ unsigned int tile_start[route_max_regions];
+  __shared__ unsigned int run_start[route_max_regions];
+  __shared__ unsigned int warp_sums[BlockSize / 32];
+
+  std::uint32_t const P           = geometry.num_ranks;
+  std::uint32_t const R           = geometry.num_regions;
+  std::uint32_t const cap         = geometry.segment_capacity;
+  std::uint32_t const num_buckets = P * R;
+
+  for (index_type base = index_type{blockIdx.x} * tile; base < n;
+       base += index_type{gridDim.x} * tile) {
+    for (std::uint32_t b = threadIdx.x; b < num_buckets; b += BlockSize) {
+      tile_hist[b] = 0;
+    }
+    __syncthreads();
+
+    using input_type = decltype(read_input(first, index_type{0}));
+    uninitialized<input_type> val[items];
+    std::uint32_t bucket[items];
+    std::uint32_t rank[items];
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
+      if (idx < n) { val[j].value = read_input(first, idx); }
+    }
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
+      bucket[j]            = 0xffffffffu;
+      if (idx < n) {
+        key_type key;
+        if constexpr (KeysOnly) {
+          key = static_cast<key_type>(val[j].value);
+        } else {
+          key = static_cast<key_type>(Engine::key_of(engine.heterogeneous_value(val[j].value)));
+        }
+        auto const owner  = exchange_owner(exchange_key_bits(key), geometry.salt, P);
+        auto const region = regions(engine.make_cursor(key).slot);
+        bucket[j]         = owner * R + region;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      if (bucket[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[bucket[j]], 1u); }
+    }
+    __syncthreads();
+    {
+      unsigned int held[buckets_per_thread];
+      unsigned int sum = 0;
+#pragma unroll
+      for (int i = 0; i < buckets_per_thread; ++i) {
+        std::uint32_t const b = threadIdx.x * buckets_per_thread + i;
+        held[i]               = b < num_buckets ? tile_hist[b] : 0u;
+        sum += held[i];
+      }
+      unsigned int inclusive = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned int const up = __shfl_up_sync(0xffffffffu, inclusive, d);
+        if ((threadIdx.x & 31) >= d) { inclusive += up; }
+      }
+      if ((threadIdx.x & 31) == 31) { warp_sums[threadIdx.x >> 5] = inclusive; }
+      __syncthreads();
+      unsigned int running = inclusive - sum;
+      for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) {
+        running += warp_sums[w];
+      }
+#pragma unroll
+      for (int i = 0; i < buckets_per_thread; ++i) {
+        std::uint32_t const b = threadIdx.x * buckets_per_thread + i;
+        if (b < num_buckets) {
+          tile_start[b] = running;
+          run_start[b]  = held[i] ? atomicAdd(&counts_local[b], held[i]) : 0u;
+          running += held[i];
+        }
+      }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      if (bucket[j] != 0xffffffffu) {
+        unsigned int const pos = tile_start[bucket[j]] + rank[j];
+        if constexpr (KeysOnly) {
+          stage[pos]  = static_cast<key_type>(val[j].value);
+          origin[pos] = static_cast<std::uint32_t>(base + index_type{j} * BlockSize + threadIdx.x);
+        } else {
+          stage[pos] = engine.native_value(engine.heterogeneous_value(val[j].value));
+        }
+        bucket_of[pos] = static_cast<std::uint16_t>(bucket[j]);
+      }
+    }
+    __syncthreads();
+
+    auto const count = static_cast<unsigned int>((n - base) < tile ? (n - base) : tile);
+    for (unsigned int pos = threadIdx.x; pos < count; pos += BlockSize) {
+      std::uint32_t const b     = bucket_of[pos];
+      std::uint64_t const where = std::uint64_t{run_start[b]} + (pos - tile_start[b]);
+      if (where < cap) {
+        std::uint32_t const owner  = b / R;
+        std::uint32_t const region = b - owner * R;
+        auto* const segment =
+          static_cast<elem_type*>(peers.base[owner]) +
+          (std::uint64_t{region} * P + geometry.my_rank) * cap;
+        segment[where] = stage[pos];
+        // the tile's 4096 positions are written together, so these scattered 4-byte stores merge
+        // into full lines in L2; the return trip then GATHERS by position with coalesced output
+        if constexpr (KeysOnly) {
+          position_local[origin[pos]] = static_cast<std::uint32_t>(std::uint64_t{b} * cap + where);
+        }
+      } else {
+        unsigned int const at = atomicAdd(spill_count, 1u);
+        if (at < spill_capacity) {
+          static_cast<elem_type*>(spill)[at] = stage[pos];
+          if constexpr (KeysOnly) { spill_index[at] = origin[pos]; }
+        }
+        if constexpr (KeysOnly) { position_local[origin[pos]] = 0xffffffffu; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+/// Tells every owner how many elements this rank put into each of its segments there, and every
+/// peer how many elements this rank spilled (peers need to agree on running the fallback).
+template <typename Geometry>  // a template only so that this header-defined kernel has vague linkage
+CUCO_KERNEL void exchange_publish_kernel(unsigned int const* counts_local,
+                                         unsigned int const* spill_count,
+                                         exchange_peers counts_recv,  ///< owners' [R * P] arrays
+                                         exchange_peers spill_flags,  ///< peers' [P] arrays
+                                         Geometry geometry)
+{
+  std::uint32_t const P = geometry.num_ranks, R = geometry.num_regions;
+  for (std::uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < P * R; b += gridDim.x * blockDim.x) {
+    std::uint32_t const owner = b / R, region = b - owner * R;
+    unsigned int const filled = counts_local[b];
+    static_cast<unsigned int*>(counts_recv.base[owner])[region * P + geometry.my_rank] =
+      filled < geometry.segment_capacity ? filled : geometry.segment_capacity;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < P) {
+    static_cast<unsigned int*>(spill_flags.base[threadIdx.x])[geometry.my_rank] = *spill_count;
+  }
+}
+
+/// Owner side of a routed lookup: probes the keys of segment g = region * P + source and stores the
+/// results straight into the source's result buffer (peer store) at the key's source-side position.
+template <int BlockSize, int KeysPerThread, int ChunkSlots, typename Result, typename Engine, typename Emit>
+CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
+  typename Engine::key_type const* segments,
+  unsigned int const* counts_recv,
+  exchange_peers results,  ///< sources' result buffers, source-side layout
+  exchange_geometry geometry,
+  Engine engine,
+  Emit emit)
+{
+  using slot_type = typename Engine::value_type;
+  using key_type  = typename Engine::key_type;
+  using cursor    = typename Engine::cursor;
+  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
+  constexpr auto policy     = load_policy::readonly;
+
+  std::uint32_t const segment = blockIdx.y;
+  std::uint32_t const region  = segment / geometry.num_ranks;
+  std::uint32_t const source  = segment - region * geometry.num_ranks;
+  index_type const count      = counts_recv[segment];
+  index_type const tile_base  = index_type{blockIdx.x} * tile;
+  if (tile_base >= count) { return; }
+
+  key_type const* const in = segments + std::uint64_t{segment} * geometry.segment_capacity;
+  Result* const out        = static_cast<Result*>(results.base[source]) +
+                      (std::uint64_t{geometry.my_rank} * geometry.num_regions + region) *
+                        geometry.segment_capacity;
+
+  uninitialized<key_type> key[KeysPerThread];
+  cursor cur[KeysPerThread];
+  unsigned pending = 0;
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+    if (idx < count) {
+      key[j].value = read_input(in, idx);
+      pending |= 1u << j;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    if (pending & (1u << j)) { cur[j] = engine.make_cursor(key[j].value); }
+  }
+  // first probe of every key, straight line: all sector loads in flight, then all scans
+  {
+    raw_chunk<ChunkSlots * Engine::slot_bytes> raw[KeysPerThread];
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (pending & (1u << j)) { raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < KeysPerThread; ++j) {
+      if (pending & (1u << j)) {
+        index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+        int const begin_off =
+          static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
+        int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
+        bool done       = false;
+#pragma unroll
+        for (int i = 0; i < ChunkSlots; ++i) {
+          if (!done && i >= begin_off && i < begin_off + valid) {
+            auto const slot  = chunk_slot<slot_type>(raw[j], i);
+            auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
+            if (state == equal_result::EQUAL) {
+              out[idx] = static_cast<Result>(emit.hit(slot));
+              done     = true;
+            } else if (state == equal_result::EMPTY) {
+              out[idx] = static_cast<Result>(emit.miss());
+              done     = true;
+            }
+          }
+        }
+        if (done) {
+          pending &= ~(1u << j);
+        } else {
+          engine.advance(cur[j], valid);
+        }
+      }
+    }
+  }
+  // leftovers (home sector full of other keys): warp-converged rounds, lowest pending key per lane
+  while (__any_sync(0xffffffffu, pending != 0)) {
+    if (pending != 0) {
+      int const jj = __ffs(pending) - 1;
+      key_type k   = key[0].value;
+      cursor c     = cur[0];
+#pragma unroll
+      for (int j = 1; j < KeysPerThread; ++j) {
+        if (j == jj) {
+          k = key[j].value;
+          c = cur[j];
+        }
+      }
+      index_type const idx = tile_base + index_type{jj} * BlockSize + threadIdx.x;
+      auto const raw       = engine.template load_chunk<ChunkSlots, policy>(c);
+      int const begin_off  = static_cast<int>(c.slot - Engine::template chunk_begin<ChunkSlots>(c));
+      int const valid      = engine.template chunk_valid<ChunkSlots>(c);
+      bool done            = false;
+#pragma unroll
+      for (int i = 0; i < ChunkSlots; ++i) {
+        if (!done && i >= begin_off && i < begin_off + valid) {
+          auto const slot  = chunk_slot<slot_type>(raw, i);
+          auto const state = engine.classify_lookup(k, Engine::key_of(slot));
+          if (state == equal_result::EQUAL) {
+            out[idx] = static_cast<Result>(emit.hit(slot));
+            done     = true;
+          } else if (state == equal_result::EMPTY) {
+            out[idx] = static_cast<Result>(emit.miss());
+            done     = true;
+          }
+        }
+      }
+      if (done) {
+        pending &= ~(1u << jj);
+      } else {
+        engine.advance(c, valid);
+#pragma unroll
+        for (int j = 0; j < KeysPerThread; ++j) {
+          if (j == jj) { cur[j] = c; }
+        }
+      }
+    }
+  }
+}
+
+/// Source side of a routed lookup: results came back in source-side segment order; every input
+/// position fetches its own (coalesced stores, gathers that stay within the tile's runs).
+template <typename Result, typename OutputIt>
+CUCO_KERNEL __launch_bounds__(256) void exchange_unpermute_kernel(Result const* results,
+                                                                  std::uint32_t const* position_local,
+                                                                  index_type n,
+                                                                  OutputIt out)
+{
+  constexpr int items = 4;  // independent gathers in flight per thread
+  for (index_type base = index_type{blockIdx.x} * (256 * items); base < n;
+       base += index_type{gridDim.x} * (256 * items)) {
+    std::uint32_t position[items];
+    Result value[items];
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const idx = base + index_type{j} * 256 + threadIdx.x;
+      position[j]          = idx < n ? __ldcs(position_local + idx) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      if (position[j] != 0xffffffffu) { value[j] = results[position[j]]; }
+    }
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const idx = base + index_type{j} * 256 + threadIdx.x;
+      if (position[j] != 0xffffffffu) { *(out + idx) = value[j]; }
+    }
+  }
 }
 
 // =================================================================================================

@@ -440,6 +440,11 @@ class static_map {
                                   impl_->storage_ref()};
   }
 
+  /// b200 extension (no reference counterpart): the engine behind this container, used by the
+  /// exchange path of hash-partitioned multi-GPU tables (include/cuco/b200/bulk_engine.cuh).
+  [[nodiscard]] impl_type& b200_engine() noexcept { return *impl_; }
+  [[nodiscard]] impl_type const& b200_engine() const noexcept { return *impl_; }
+
  private:
   std::unique_ptr<impl_type> impl_;
   mapped_type empty_value_sentinel_;

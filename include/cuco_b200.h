@@ -221,6 +221,80 @@ int cuco_b200_partition_scatter(const void* keys,
                                 void* values_out,
                                 int64_t* src_index,
                                 void* stream);
+/* ---- fused exchange path (native build only; no reference counterpart) --------------------------
+ * One routing kernel groups a rank's batch by (owner rank, L2 region of the owner's shard) and
+ * stores it straight into the owners' segment buffers through peer pointers (NVLink P2P), so the
+ * all-to-all and the region grouping of the owner's probe pass are the same kernel; lookups return
+ * the same way (the owner's lookup kernel stores results into the source's result buffer).
+ * All shards must have the same capacity. Buffers (per rank, P = num_ranks, R = num_regions,
+ * cap = segment_capacity; "peer" = addressable from every rank, e.g. torch symmetric memory):
+ *   segments  peer, P*R*cap elements (slot size for mutations, key size for lookups);
+ *             owner-side index (region*P + source)*cap + pos
+ *   counts    peer, uint32[R*P]   fill of each received segment, written by its source
+ *   flags     peer, uint32[P]     flags[s] = elements rank s spilled in this call
+ *   results   peer, P*R*cap results; source-side index (owner*R + region)*cap + pos
+ *   counts_local uint32[P*R], position_local uint32[n_max] (where each routed key's result will
+ *   arrive, source-side index; 0xffffffff = spilled), spill / spill_index [spill_capacity],
+ *   spill_count uint32[1]        local scratch of the source
+ * Call order per bulk operation (every rank, same stream): barrier; exchange_route; barrier;
+ * exchange_mutate or exchange_lookup; (lookups) barrier; exchange_unpermute. A caller that finds a
+ * non-zero flag must finish the spilled elements through another path (cucollections_b200/
+ * partitioned.py uses the all_to_all fallback). */
+int cuco_b200_exchange_plan(cuco_b200_table* t,
+                            int64_t n_max,
+                            int num_ranks,
+                            uint32_t* num_regions,
+                            uint32_t* segment_capacity,
+                            uint32_t* spill_capacity);
+int cuco_b200_exchange_route(cuco_b200_table* t,
+                             const void* keys,
+                             const void* values,
+                             int64_t n,
+                             int keys_only,
+                             uint32_t num_regions,
+                             uint32_t segment_capacity,
+                             uint32_t spill_capacity,
+                             int num_ranks,
+                             int my_rank,
+                             uint64_t salt,
+                             void* const* peer_segments,
+                             void* const* peer_counts,
+                             void* const* peer_flags,
+                             void* counts_local,
+                             void* position_local,
+                             void* spill,
+                             void* spill_index,
+                             void* spill_count,
+                             void* stream);
+/* reduce_op < 0: insert; otherwise insert_or_apply with cuco_b200_reduce_op */
+int cuco_b200_exchange_mutate(cuco_b200_table* t,
+                              const void* segments,
+                              const void* counts_recv,
+                              uint32_t num_regions,
+                              uint32_t segment_capacity,
+                              int num_ranks,
+                              int reduce_op,
+                              void* stream);
+/* what: 0 find (results have the payload / key type), 1 contains (bytes) */
+int cuco_b200_exchange_lookup(cuco_b200_table* t,
+                              const void* segments,
+                              const void* counts_recv,
+                              void* const* peer_results,
+                              uint32_t num_regions,
+                              uint32_t segment_capacity,
+                              int num_ranks,
+                              int my_rank,
+                              int what,
+                              void* stream);
+/* out[i] = results[position_local[i]] for the n keys routed by the matching exchange_route call */
+int cuco_b200_exchange_unpermute(cuco_b200_table* t,
+                                 const void* results,
+                                 const void* position_local,
+                                 int64_t n,
+                                 void* out,
+                                 int what,
+                                 void* stream);
+
 /* out[index[i]] = in[i] for i < n (elem_bytes in {1,4,8}); un-permutes routed lookup results. */
 int cuco_b200_scatter_by_index(
   const void* in, const int64_t* index, void* out, int elem_bytes, int64_t n, void* stream);

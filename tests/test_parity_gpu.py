@@ -12,6 +12,7 @@ import torch
 
 import cucollections_b200 as cb
 from cucollections_b200 import _cabi
+from cucollections_b200 import partitioned as cbp
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -426,3 +427,178 @@ def test_host_buffer_insert_of_aos_pairs(native_lib):
     assert t.size() == n
     assert torch.equal(out, keys * 3)
     t.close()
+
+
+class _SimulatedRank:
+    """One 'rank' of the fused exchange path, with every rank living on the same GPU: peer pointers
+    are ordinary device pointers, so the routing / probe / return kernels run exactly as they do over
+    NVLink (the multi-process version is cucollections_b200/partitioned.py::FusedExchange)."""
+
+    def __init__(self, lib, kind, n_total, n_batch, P, me):
+        import ctypes as C
+        self.C, self.lib, self.P, self.me = C, lib, P, me
+        self.table = make(kind, lib, n=n_total // P + n_total // (8 * P) + 64, load_factor=0.5)
+        r, cap, sp = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib.check(lib.exchange_plan(self.table._handle, n_batch, P, C.byref(r), C.byref(cap), C.byref(sp)))
+        self.R, self.cap, self.spill_cap = r.value, cap.value, sp.value
+        k = cb.KINDS[kind]
+        self.slot_bytes = k.key.itemsize + (k.value.itemsize if k.value is not None else 0)
+        seg = P * self.R * self.cap
+        z = dict(device="cuda")
+        self.segments = torch.zeros(seg * self.slot_bytes, dtype=torch.uint8, **z)
+        self.counts = torch.zeros(self.R * P, dtype=torch.int32, **z)
+        self.flags = torch.zeros(P, dtype=torch.int32, **z)
+        self.results = torch.zeros(seg * 8, dtype=torch.uint8, **z)
+        self.counts_local = torch.zeros(P * self.R, dtype=torch.int32, **z)
+        self.position_local = torch.zeros(max(1, n_batch), dtype=torch.int32, **z)
+        self.spill = torch.zeros(self.spill_cap * self.slot_bytes, dtype=torch.uint8, **z)
+        self.spill_index = torch.zeros(self.spill_cap, dtype=torch.int32, **z)
+        self.spill_count = torch.zeros(1, dtype=torch.int32, **z)
+
+    def peers(self, ranks, attr):
+        C = self.C
+        return (C.c_void_p * self.P)(*[getattr(r, attr).data_ptr() for r in ranks])
+
+    def route(self, ranks, keys, values, keys_only):
+        C = self.C
+        vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        self.lib.check(self.lib.exchange_route(
+            self.table._handle, vp(keys), vp(values), keys.shape[0], int(keys_only), self.R, self.cap,
+            self.spill_cap, self.P, self.me, cbp.DEFAULT_SALT, self.peers(ranks, "segments"),
+            self.peers(ranks, "counts"), self.peers(ranks, "flags"), vp(self.counts_local), vp(self.position_local),
+            vp(self.spill), vp(self.spill_index), vp(self.spill_count), None))
+
+    def mutate(self, op=-1):
+        C = self.C
+        self.lib.check(self.lib.exchange_mutate(self.table._handle, C.c_void_p(self.segments.data_ptr()),
+                                                C.c_void_p(self.counts.data_ptr()), self.R, self.cap, self.P, op,
+                                                None))
+
+    def lookup(self, ranks, what):
+        C = self.C
+        self.lib.check(self.lib.exchange_lookup(self.table._handle, C.c_void_p(self.segments.data_ptr()),
+                                                C.c_void_p(self.counts.data_ptr()), self.peers(ranks, "results"),
+                                                self.R, self.cap, self.P, self.me, what, None))
+
+    def unpermute(self, out, what):
+        C = self.C
+        self.lib.check(self.lib.exchange_unpermute(self.table._handle, C.c_void_p(self.results.data_ptr()),
+                                                   C.c_void_p(self.position_local.data_ptr()), out.shape[0],
+                                                   C.c_void_p(out.data_ptr()), what, None))
+
+
+@pytest.mark.parametrize("kind,P", [(_cabi.MAP_I64_LP1, 3), (_cabi.MAP_I64_DH8, 2), (_cabi.MAP_I32_LP4, 4),
+                                    (_cabi.SET_I64_DH4, 2)])
+def test_fused_exchange_kernels_with_simulated_ranks(kind, P, native_lib):
+    """Routing by (owner, region) into the owners' buffers, region-ordered probe of the received
+    segments, lookups answered into the sources' result buffers and un-permuted: the union of the
+    shards must behave like ONE table (the oracle) holding every rank's batch."""
+    k = cb.KINDS[kind]
+    is_map = k.value is not None
+    n = 50_000  # per rank
+    try:
+        native_lib.set_blocking(1, -64)  # 64 KiB regions: dozens of regions per shard
+        ranks = [_SimulatedRank(native_lib, kind, n * P, n, P, me) for me in range(P)]
+        ref = oracle.Table.for_kind(kind, 2 * n * P, 0.0)
+        batches = []
+        for me in range(P):
+            keys = keyset(kind, n, 40 + me, hi=2 * n)  # overlaps between ranks and duplicates within
+            vals = keys * 7 + 3
+            batches.append((keys, vals))
+            ref.insert(keys, vals if is_map else None)
+            ranks[me].route(ranks, dev(keys, k.key), dev(vals, k.value) if is_map else None, False)
+        torch.cuda.synchronize()
+        for r in ranks:
+            assert int(r.flags.sum().item()) == 0  # nothing spilled
+            r.mutate()
+        torch.cuda.synchronize()
+        assert sum(r.table.size() for r in ranks) == ref.size()
+        sizes = [r.table.size() for r in ranks]
+        assert min(sizes) > 0.7 * ref.size() / P  # owner hash balances the shards
+        # lookups: half present, half absent, per rank
+        queries = [np.concatenate([batches[me][0][: n // 2], keyset(kind, n // 2, 60 + me, hi=2 * n) + 4 * n])
+                   for me in range(P)]
+        for what in (0, 1):
+            for me in range(P):
+                ranks[me].route(ranks, dev(queries[me], k.key), None, True)
+            torch.cuda.synchronize()
+            for r in ranks:
+                r.lookup(ranks, what)
+            torch.cuda.synchronize()
+            for me in range(P):
+                if what == 0:
+                    out = torch.full((queries[me].shape[0],), -7, dtype=k.value if is_map else k.key, device="cuda")
+                    ranks[me].unpermute(out, 0)
+                    assert np.array_equal(out.cpu().numpy().astype(np.int64), ref.find(queries[me])), (what, me)
+                else:
+                    out = torch.full((queries[me].shape[0],), 9, dtype=torch.uint8, device="cuda")
+                    ranks[me].unpermute(out, 1)
+                    assert np.array_equal(out.cpu().numpy().astype(bool), ref.contains(queries[me])), (what, me)
+        if is_map:  # aggregate variant: sum of ones per key over every rank's batch
+            for r in ranks:
+                r.table.clear()
+            agg = oracle.Table.for_kind(kind, 2 * n * P, 0.0, empty_value=0)
+            aggs = [make(kind, native_lib, n=n * P, load_factor=0.5, empty_value=0) for _ in range(P)]
+            for me in range(P):
+                ranks[me].table.close()
+                ranks[me].table = aggs[me]
+                ones = np.ones(n, dtype=np.int64)
+                agg.insert_or_apply(batches[me][0], ones, oracle.PLUS)
+                ranks[me].route(ranks, dev(batches[me][0], k.key), dev(ones, k.value), False)
+            torch.cuda.synchronize()
+            for r in ranks:
+                r.mutate(_cabi.PLUS)
+            torch.cuda.synchronize()
+            got = {}
+            for r in ranks:
+                ks, vs = r.table.retrieve_all()
+                got.update(zip(ks.cpu().tolist(), vs.cpu().tolist()))
+            wk, wv = agg.retrieve_all()
+            assert got == dict(zip(wk.tolist(), wv.tolist()))
+        for r in ranks:
+            r.table.close()
+    finally:
+        native_lib.set_blocking(-1, 16)
+
+
+def test_fused_exchange_spills_when_a_segment_overflows(native_lib):
+    """A batch made of one hot key overflows its (owner, region) segment: the surplus must land in the
+    spill list with its source indices, and the flags must tell every peer."""
+    P, n = 2, 40_000
+    ranks = [_SimulatedRank(native_lib, _cabi.MAP_I64_LP1, n * P, n, P, me) for me in range(P)]
+    keys = np.full(n, 12345, dtype=np.int64)
+    ranks[0].route(ranks, dev(keys, torch.int64), None, True)
+    torch.cuda.synchronize()
+    spilled = int(ranks[0].spill_count.item())
+    assert spilled == n - ranks[0].cap
+    assert [int(r.flags[0].item()) for r in ranks] == [spilled, spilled]
+    routed = int(torch.clamp(ranks[0].counts_local, max=ranks[0].cap).sum().item())
+    assert routed == ranks[0].cap
+    idx = ranks[0].spill_index[:spilled].cpu().numpy()
+    assert len(set(idx.tolist())) == spilled and idx.min() >= 0 and idx.max() < n
+    marked = (ranks[0].position_local.cpu().numpy().view(np.uint32) == 0xFFFFFFFF).nonzero()[0]
+    assert sorted(marked.tolist()) == sorted(idx.tolist())
+    for r in ranks:
+        r.table.close()
+
+
+def test_partitioned_table_on_all_visible_gpus():
+    """tests/multi_gpu_check.py under torchrun, one rank per visible GPU (needs >= 2): fused P2P
+    exchange == all_to_all routing == ONE table over the union of all ranks' batches."""
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+    gpus = torch.cuda.device_count()
+    if gpus < 2:
+        pytest.skip("needs at least 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          str(root / "tests" / "multi_gpu_check.py"), "1000000"],
+                         capture_output=True, text=True, timeout=900)
+    assert "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.returncode == 0

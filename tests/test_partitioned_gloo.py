@@ -61,6 +61,9 @@ class _OracleTable:
     def size(self):
         return self.t.size()
 
+    def _payload_dtype(self):
+        return torch.int64
+
     def clear_async(self):
         self.t.clear()
 
