@@ -476,8 +476,10 @@ def bench(args, lib, impl):
         "gpu_launches": (7 if routing == "fused" else 8) * args.steps * world,
         "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled in multi-GPU mode"]},
     }
-    if table.fused is not None and table.fused.trace is not None and rank == 0:
-        result["exchange_trace_ms"] = table.fused.trace_summary()
+    if table.fused is not None and table.fused.trace is not None:
+        traces = [None] * world
+        dist.all_gather_object(traces, table.fused.trace_summary())
+        result["exchange_trace_ms"] = traces  # one dict per rank
     table.close()
     dist.barrier()
     return result

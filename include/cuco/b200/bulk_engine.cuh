@@ -651,11 +651,9 @@ class table_engine {
     void* base        = storage_.data();
     auto const window = this->window_bytes();
 
-    if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable &&
-                  std::is_same_v<StencilIt, thrust::constant_iterator<bool>> &&
-                  std::is_same_v<Predicate, always_true>) {
+    if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable) {
       if (this->fast_path_ok(true) && this->blocking_pays(n)) {
-        this->blocked_mutate<Counted>(in, n, counter, engine, action, stream);
+        this->blocked_mutate<Counted>(in, n, st, pred, counter, engine, action, stream);
         return;
       }
     }
@@ -753,9 +751,16 @@ class table_engine {
 
   /// L2-blocked mutation: route the batch by table region (pass 1), then probe the regions in
   /// order with the region's slots resident in L2 (pass 2). See bulk_kernels.cuh.
-  template <bool Counted, typename InputIt, typename EngineT, typename Action>
+  template <bool Counted,
+            typename InputIt,
+            typename StencilIt,
+            typename Predicate,
+            typename EngineT,
+            typename Action>
   void blocked_mutate(InputIt in,
                       cuco::detail::index_type n,
+                      StencilIt stencil,
+                      Predicate pred,
                       size_type* counter,
                       EngineT const& engine,
                       Action action,
@@ -783,8 +788,15 @@ class table_engine {
 
     constexpr int chunk = EngineT::sector_chunk_slots;
     {
-      auto const kernel =
-        route_kernel<route_block_size, chunk, Counted, InputIt, size_type, EngineT, Action>;
+      auto const kernel = route_kernel<route_block_size,
+                                       chunk,
+                                       Counted,
+                                       InputIt,
+                                       StencilIt,
+                                       Predicate,
+                                       size_type,
+                                       EngineT,
+                                       Action>;
       constexpr std::size_t smem = route_smem_bytes<route_block_size, value_type>();
       static bool const configured = [&] {
         return cudaFuncSetAttribute(
@@ -795,7 +807,7 @@ class table_engine {
         cuco::detail::int_div_ceil(n, index_type{route_block_size} * route_items_per_thread);
       auto const grid = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
       kernel<<<grid, route_block_size, smem, stream.get()>>>(
-        in, n, segments, counts, regions, segment_capacity, counter, engine, action);
+        in, n, stencil, pred, segments, counts, regions, segment_capacity, counter, engine, action);
     }
     {
       auto run = [&](auto kpt, auto cas_first) {
@@ -851,9 +863,11 @@ class table_engine {
                  "exchange batches are limited to 2^32 - 1 elements per rank");
     auto const& t          = tuning();
     auto const table_bytes = static_cast<std::uint64_t>(storage_.capacity()) * sizeof(value_type);
-    auto const max_regions = static_cast<std::uint64_t>(route_max_regions / num_ranks);
-    auto const regions     = std::max<std::uint64_t>(
-      1, std::min<std::uint64_t>(max_regions, (table_bytes + t.region_bytes - 1) / t.region_bytes));
+    // Fine-grained exchange (the router also groups by L2 region of the owner's shard) while the
+    // runs stay long enough for NVLink: a tile of 4096 elements over P * R buckets. Beyond 512
+    // buckets the router groups by owner only (16 KB runs) and the owner regroups locally.
+    auto const local_regions = std::max<std::uint64_t>(1, (table_bytes + t.region_bytes - 1) / t.region_bytes);
+    auto const regions       = local_regions * num_ranks <= 512 ? local_regions : std::uint64_t{1};
     auto const segments = regions * static_cast<std::uint64_t>(num_ranks);
     auto const mean     = (static_cast<std::uint64_t>(n_max) + segments - 1) / segments;
     return exchange_plan{static_cast<std::uint32_t>(regions),
@@ -946,6 +960,20 @@ class table_engine {
     CUCO_EXPECTS(this->fast_path_ok(true), "the exchange path needs container-owned storage without tombstones");
     auto const& t           = tuning();
     auto const capacity     = static_cast<std::uint64_t>(storage_.capacity());
+    if (plan.num_regions == 1 && num_ranks > 1) {
+      // owner-only routing: the received segments are an ordinary (gappy) batch; the bulk path
+      // regroups it by L2 region locally when that pays
+      auto const virtual_n = index_type{plan.segment_capacity} * num_ranks;
+      this->template mutate<false>(segments,
+                                   virtual_n,
+                                   thrust::counting_iterator<index_type>{0},
+                                   segment_live{counts_recv, plan.segment_capacity},
+                                   static_cast<size_type*>(nullptr),
+                                   ref,
+                                   action,
+                                   stream);
+      return;
+    }
     constexpr int chunk     = engine_t::sector_chunk_slots;
     constexpr int kpt       = 4;
     auto const kernel       = blocked_mutate_kernel<block_size, kpt, chunk, true, false, size_type, engine_t, Action>;

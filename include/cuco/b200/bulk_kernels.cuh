@@ -643,15 +643,33 @@ constexpr std::size_t route_smem_bytes() noexcept
   return std::size_t{BlockSize} * route_items_per_thread * (sizeof(Slot) + sizeof(std::uint16_t));
 }
 
+/// Predicate over a virtual index space made of fixed-capacity segments: element i exists iff its
+/// offset inside segment i / capacity is below that segment's fill count (exchange buffers).
+struct segment_live {
+  unsigned int const* counts;
+  std::uint32_t segment_capacity;
+
+  __device__ bool operator()(index_type i) const noexcept
+  {
+    auto const segment = static_cast<std::uint32_t>(i / segment_capacity);
+    auto const local   = static_cast<std::uint32_t>(i - index_type{segment} * segment_capacity);
+    return local < counts[segment];
+  }
+};
+
 template <int BlockSize,
           int ChunkSlots,
           bool Counted,
           typename InputIt,
+          typename StencilIt,
+          typename Predicate,
           typename Counter,
           typename Engine,
           typename Action>
 CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
                                                            index_type n,
+                                                           StencilIt stencil,
+                                                           Predicate pred,
                                                            typename Engine::value_type* segments,
                                                            unsigned int* region_counts,
                                                            region_map regions,
@@ -688,16 +706,19 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
     std::uint32_t region[items];
     std::uint32_t rank[items];
     // all loads of the tile in flight first; hashing starts when the first one lands
+    unsigned live = 0;
 #pragma unroll
     for (int j = 0; j < items; ++j) {
       index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
-      if (idx < n) { val[j].value = engine.heterogeneous_value(read_input(first, idx)); }
+      if (idx < n && pred(*(stencil + idx))) {
+        val[j].value = engine.heterogeneous_value(read_input(first, idx));
+        live |= 1u << j;
+      }
     }
 #pragma unroll
     for (int j = 0; j < items; ++j) {
-      index_type const idx = base + index_type{j} * BlockSize + threadIdx.x;
-      region[j]            = 0xffffffffu;
-      if (idx < n) { region[j] = regions(engine.make_cursor(Engine::key_of(val[j].value)).slot); }
+      region[j] = 0xffffffffu;
+      if (live & (1u << j)) { region[j] = regions(engine.make_cursor(Engine::key_of(val[j].value)).slot); }
     }
 #pragma unroll
     for (int j = 0; j < items; ++j) {
@@ -749,7 +770,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
     }
     __syncthreads();
 
-    auto const count = static_cast<unsigned int>((n - base) < tile ? (n - base) : tile);
+    // staged elements of this tile = end of the last region's run
+    unsigned int const count = tile_start[num_regions - 1] + tile_hist[num_regions - 1];
     for (unsigned int pos = threadIdx.x; pos < count; pos += BlockSize) {
       std::uint32_t const r     = owner[pos];
       std::uint64_t const where = std::uint64_t{run_start[r]} + (pos - tile_start[r]);

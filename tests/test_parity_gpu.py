@@ -487,9 +487,11 @@ class _SimulatedRank:
                                                    C.c_void_p(out.data_ptr()), what, None))
 
 
-@pytest.mark.parametrize("kind,P", [(_cabi.MAP_I64_LP1, 3), (_cabi.MAP_I64_DH8, 2), (_cabi.MAP_I32_LP4, 4),
-                                    (_cabi.SET_I64_DH4, 2)])
-def test_fused_exchange_kernels_with_simulated_ranks(kind, P, native_lib):
+@pytest.mark.parametrize("kind,P,region_kib", [
+    (_cabi.MAP_I64_LP1, 3, 64), (_cabi.MAP_I64_DH8, 2, 64), (_cabi.MAP_I32_LP4, 4, 64), (_cabi.SET_I64_DH4, 2, 64),
+    (_cabi.MAP_I64_LP1, 4, 4),   # > 512 (owner, region) buckets: owner-only routing + local regrouping
+    (_cabi.MAP_I32_LP4, 8, 2)])
+def test_fused_exchange_kernels_with_simulated_ranks(kind, P, region_kib, native_lib):
     """Routing by (owner, region) into the owners' buffers, region-ordered probe of the received
     segments, lookups answered into the sources' result buffers and un-permuted: the union of the
     shards must behave like ONE table (the oracle) holding every rank's batch."""
@@ -497,8 +499,9 @@ def test_fused_exchange_kernels_with_simulated_ranks(kind, P, native_lib):
     is_map = k.value is not None
     n = 50_000  # per rank
     try:
-        native_lib.set_blocking(1, -64)  # 64 KiB regions: dozens of regions per shard
+        native_lib.set_blocking(1, -region_kib)  # small regions: dozens to hundreds per shard
         ranks = [_SimulatedRank(native_lib, kind, n * P, n, P, me) for me in range(P)]
+        assert (ranks[0].R == 1) == (region_kib < 64)
         ref = oracle.Table.for_kind(kind, 2 * n * P, 0.0)
         batches = []
         for me in range(P):
