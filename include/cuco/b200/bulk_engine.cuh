@@ -729,6 +729,7 @@ class table_engine {
   {
     auto const& t = tuning();
     if (t.blocked == 0 || n <= 0) { return false; }
+    if (n >= (cuco::detail::index_type{1} << 32)) { return false; }  // segment counters are 32-bit
     auto const bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
     if (bytes / route_max_regions > (std::size_t{48} << 20)) { return false; }
     if (t.blocked > 0) { return true; }
