@@ -5,17 +5,23 @@
 // launchers (detail/static_map/static_map.inl:279-358, detail/static_map/helpers.cuh:50-114).
 // Same stream-ordered contract: `*_async` never synchronise, the counting variants return after one
 // device->host copy. Differences in how the work is issued:
-//   * persistent grids sized to the resident-CTA count of the 148 SMs, several keys per thread,
-//     instead of one 128-thread block per 128/cg_size keys;
+//   * thread-per-key kernels with several probes in flight per thread, one CTA per tile (measured
+//     10-30 % faster than a persistent grid for random probes), instead of one 128-thread block per
+//     128/cg_size keys;
 //   * contiguous iterators are unwrapped to raw pointers so inputs stream through 128-bit
 //     non-allocating loads;
+//   * mutations of tables far beyond L2 take the L2-blocked path when the batch is dense enough:
+//     route the batch by 16 MB table region, then probe region by region (bulk_kernels.cuh);
 //   * the success counter of the synchronous insert lives with the container (the reference
-//     cudaMallocs and frees one per call, impl.cuh:337-347);
+//     cudaMallocs and frees one per call, impl.cuh:337-347), as does the staging buffer of the
+//     blocked path (grow-only, ~1.07 x batch bytes);
 //   * tables small enough to live in L2 get an access-policy window on the launch (persisting
-//     lines for the table, streaming for everything else).
-// Run-time tuning (keys per thread, CAS-first, chunk width) is compiled in only when
-// CUCO_B200_TUNABLE is defined (the C-ABI library used by bench.py does); otherwise the defaults
-// below are the only instantiations.
+//     lines for the table, streaming for everything else);
+//   * hash-partitioned multi-GPU tables: exchange_* members route a batch straight into the owner
+//     ranks' memory and probe / answer it there (no reference counterpart).
+// Run-time tuning (keys per thread, CAS-first, chunk width, blocked-path variants) is compiled in only
+// when CUCO_B200_TUNABLE is defined (the C-ABI library used by bench.py does, for the benchmarked
+// instantiations); otherwise the defaults below are the only instantiations.
 #pragma once
 
 #include <cuco/b200/bulk_kernels.cuh>

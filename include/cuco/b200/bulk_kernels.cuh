@@ -17,7 +17,10 @@
 //  * a slot is claimed with one CAS on the whole slot image (32/64/128 bit). With `CasFirst` the
 //    first probe of an insert is the CAS itself - no load - which is the common case at load
 //    factors <= 0.5 where the home slot is usually free.
-//  * the grid is persistent: min(#tiles, resident CTAs on all SMs), grid-stride over tiles.
+//  * one CTA per tile by default (a persistent grid-stride launch is a tuning option);
+//  * all input loads of a thread are posted before the first is consumed;
+//  * mutations of tables far beyond L2 can be routed by table region first ("L2-blocked mutation"
+//    below), and hash-partitioned multi-GPU tables route by owner rank as well ("Exchange path").
 //
 // Kernels with `generic_` prefix are the one-key-per-thread fallbacks used when the fast path's
 // preconditions do not hold (tombstones configured, padded slots, storage not 32-byte aligned).
