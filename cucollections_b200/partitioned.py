@@ -83,56 +83,73 @@ class GpuBackend:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
 
+class _Lane:
+    """One set of exchange buffers (symmetric + local scratch) sized for `n_lane` elements per rank."""
+
+
 class FusedExchange:
     """Fused routing over peer memory (cuco_b200_exchange_*, include/cuco_b200.h): one kernel groups
     the batch by (owner, L2 region of the owner's shard) and stores it into the owners' buffers over
     NVLink; the owner probes region by region; lookup results are stored back the same way. Buffers
-    live in torch symmetric memory so every rank can address every peer's copy. Native build only."""
+    live in torch symmetric memory so every rank can address every peer's copy. Native build only.
 
-    def __init__(self, table, n_max, group, device, salt):
+    `lanes` > 1 cuts every batch into that many chunks, each with its own buffer set, and software-
+    pipelines them: chunk c+1 is routed (NVLink-bound, on a side stream) while chunk c is probed on the
+    caller's stream (SM / L2-bound)."""
+
+    def __init__(self, table, n_max, group, device, salt, lanes=1):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.table, self.lib, self.device, self.salt = table, table._lib, torch.device(device), salt
         self.group = group
         self.P, self.me = dist.get_world_size(group), dist.get_rank(group)
+        self.n_max, self.K = int(n_max), max(1, int(lanes))
+        self.n_lane = -(-self.n_max // self.K)
         r, cap, spill = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        self.lib.check(self.lib.exchange_plan(table._handle, int(n_max), self.P, C.byref(r), C.byref(cap),
+        self.lib.check(self.lib.exchange_plan(table._handle, self.n_lane, self.P, C.byref(r), C.byref(cap),
                                               C.byref(spill)))
-        self.R, self.cap, self.spill_cap, self.n_max = r.value, cap.value, spill.value, int(n_max)
+        self.R, self.cap, self.spill_cap = r.value, cap.value, spill.value
         k = table.kind
         self.key_bytes = k.key.itemsize
         self.slot_bytes = self.key_bytes + (k.value.itemsize if k.value is not None else 0)
-        self.result_dtype = k.value if k.value is not None else k.key
         seg_elems = self.P * self.R * self.cap
 
         def pad(x):
             return (x + 255) // 256 * 256
 
-        self.off_segments = 0
-        self.off_counts = pad(seg_elems * self.slot_bytes)
-        self.off_flags = self.off_counts + pad(self.R * self.P * 4)
-        self.off_results = self.off_flags + pad(self.P * 4)
-        total = self.off_results + pad(seg_elems * 8)
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        off_segments = 0
+        off_counts = pad(seg_elems * self.slot_bytes)
+        off_flags = off_counts + pad(self.R * self.P * 4)
+        off_results = off_flags + pad(self.P * 4)
+        lane_bytes = off_results + pad(seg_elems * 8)
+        self.buf = symm_mem.empty(lane_bytes * self.K, dtype=torch.uint8, device=self.device)
         self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         vp = C.c_void_p * self.P
-        self.peer_segments = vp(*[p + self.off_segments for p in ptrs])
-        self.peer_counts = vp(*[p + self.off_counts for p in ptrs])
-        self.peer_flags = vp(*[p + self.off_flags for p in ptrs])
-        self.peer_results = vp(*[p + self.off_results for p in ptrs])
-        base = self.buf.data_ptr()
-        self.my_segments = C.c_void_p(base + self.off_segments)
-        self.my_counts = C.c_void_p(base + self.off_counts)
-        self.my_results = C.c_void_p(base + self.off_results)
-        self.flags = self.buf[self.off_flags:self.off_flags + self.P * 4].view(torch.int32)
-        self.flags.zero_()
-        self.counts_local = torch.zeros(self.P * self.R, dtype=torch.int32, device=self.device)
-        self.position_local = torch.empty(max(1, self.n_max), dtype=torch.int32, device=self.device)
-        self.spill = torch.empty(self.spill_cap * self.slot_bytes, dtype=torch.uint8, device=self.device)
-        self.spill_index = torch.empty(self.spill_cap, dtype=torch.int32, device=self.device)
-        self.spill_count = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.flags_host = torch.zeros(self.P, dtype=torch.int32).pin_memory()
+        self.lanes = []
+        for i in range(self.K):
+            lane, shift = _Lane(), i * lane_bytes
+            lane.id = i
+            lane.peer_segments = vp(*[p + shift + off_segments for p in ptrs])
+            lane.peer_counts = vp(*[p + shift + off_counts for p in ptrs])
+            lane.peer_flags = vp(*[p + shift + off_flags for p in ptrs])
+            lane.peer_results = vp(*[p + shift + off_results for p in ptrs])
+            base = self.buf.data_ptr() + shift
+            lane.my_segments = C.c_void_p(base + off_segments)
+            lane.my_counts = C.c_void_p(base + off_counts)
+            lane.my_results = C.c_void_p(base + off_results)
+            lane.flags = self.buf[shift + off_flags: shift + off_flags + self.P * 4].view(torch.int32)
+            lane.flags.zero_()
+            lane.counts_local = torch.zeros(self.P * self.R, dtype=torch.int32, device=self.device)
+            lane.position_local = torch.empty(max(1, self.n_lane), dtype=torch.int32, device=self.device)
+            lane.spill = torch.empty(self.spill_cap * self.slot_bytes, dtype=torch.uint8, device=self.device)
+            lane.spill_index = torch.empty(self.spill_cap, dtype=torch.int32, device=self.device)
+            lane.spill_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            lane.landed = torch.cuda.Event()
+            lane.consumed = torch.cuda.Event()
+            self.lanes.append(lane)
+        self.flags_host = torch.zeros(self.K * self.P, dtype=torch.int32).pin_memory()
+        self.side = torch.cuda.Stream(self.device) if self.K > 1 else None
         # CUCO_B200_EXCHANGE_TRACE=1: CUDA events around every stage, summarised by trace_summary()
         self.trace = [] if os.environ.get("CUCO_B200_EXCHANGE_TRACE") else None
         torch.cuda.synchronize(self.device)
@@ -145,8 +162,8 @@ class FusedExchange:
             self.trace.append((label, e))
 
     def trace_summary(self):
-        """Median milliseconds per stage label (time since the previous mark) over all traced calls
-        (mutations and lookups share the routing labels)."""
+        """Median milliseconds per stage label (time since the previous mark ON THE SAME STREAM is only
+        meaningful for lanes == 1) over all traced calls; mutations and lookups share the routing labels."""
         if not self.trace:
             return {}
         torch.cuda.synchronize(self.device)
@@ -159,77 +176,125 @@ class FusedExchange:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _barrier(self):
-        self.hdl.barrier(channel=0)
-
-    def _route(self, elems, values, n, keys_only):
-        if n > self.n_max:
-            raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
+    def _route(self, lane, elems, n, keys_only):
+        """Runs on the current stream: wait until every owner has consumed this lane, route, wait until
+        every source's segments, counts and flags have landed."""
         self._mark("begin")
-        self._barrier()  # every owner has consumed the previous exchange
+        self.hdl.barrier(channel=lane.id)
         self._mark("barrier (previous exchange consumed)")
         with torch.cuda.device(self.device):
             self.lib.check(self.lib.exchange_route(
-                self.table._handle, _vp(elems), _vp(values), n, int(keys_only), self.R, self.cap, self.spill_cap,
-                self.P, self.me, self.salt, self.peer_segments, self.peer_counts, self.peer_flags,
-                _vp(self.counts_local), _vp(self.position_local), _vp(self.spill), _vp(self.spill_index),
-                _vp(self.spill_count), self._stream()))
+                self.table._handle, _vp(elems), None, n, int(keys_only), self.R, self.cap, self.spill_cap,
+                self.P, self.me, self.salt, lane.peer_segments, lane.peer_counts, lane.peer_flags,
+                _vp(lane.counts_local), _vp(lane.position_local), _vp(lane.spill), _vp(lane.spill_index),
+                _vp(lane.spill_count), self._stream()))
         self._mark("route + publish")
-        self._barrier()  # segments, counts and flags of every source have landed
+        self.hdl.barrier(channel=lane.id)
         self._mark("barrier (segments landed)")
 
+    def _chunks(self, n):
+        return [(lo, min(n, lo + self.n_lane)) for lo in range(0, max(n, 1), self.n_lane)] if n else []
+
+    def _run(self, elems, keys_only, consume):
+        """Routes `elems` chunk by chunk (lane = chunk index mod lanes) and calls `consume(lane, lo, hi)`
+        on the caller's stream once the chunk has landed everywhere."""
+        n = elems.shape[0]
+        if n > self.n_max:
+            raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
+        main = torch.cuda.current_stream(self.device)
+        chunks = self._chunks(n) or [(0, 0)]  # an empty batch still takes part in the barriers
+        if self.side is None:
+            for i, (lo, hi) in enumerate(chunks):
+                lane = self.lanes[i % self.K]
+                self._route(lane, elems[lo:hi], hi - lo, keys_only)
+                consume(lane, lo, hi)
+            return
+        elems.record_stream(self.side)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.side.wait_event(ready)  # the batch is complete before the side stream reads it
+        for i, (lo, hi) in enumerate(chunks):
+            lane = self.lanes[i % self.K]
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(lane.consumed)  # our own owner-side work on this lane is done
+                self._route(lane, elems[lo:hi], hi - lo, keys_only)
+                lane.landed.record(self.side)
+            main.wait_event(lane.landed)
+            consume(lane, lo, hi)
+            lane.consumed.record(main)
+
     def _spilled(self):
-        """(total spilled over all ranks, spilled here): one 4*P byte read-back per bulk call."""
-        self.flags_host.copy_(self.flags, non_blocking=True)
+        """(total spilled over all ranks and lanes, [spilled here per lane]): one small read-back per
+        bulk call."""
+        for i, lane in enumerate(self.lanes):
+            self.flags_host[i * self.P:(i + 1) * self.P].copy_(lane.flags, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        mine = int(self.flags_host[self.me].item())
-        if mine > self.spill_cap:
+        mine = [int(self.flags_host[i * self.P + self.me].item()) for i in range(self.K)]
+        if max(mine) > self.spill_cap:
             raise RuntimeError("batch too skewed for the exchange buffers: spill list overflowed")
         return int(self.flags_host.sum().item()), mine
 
     def mutate(self, pairs, reduce_op=-1):
         """Routes and applies a batch of [n, 2] pairs; returns this rank's spilled pairs (or None)."""
-        n = pairs.shape[0]
-        self._route(pairs, None, n, False)
-        with torch.cuda.device(self.device):
-            self.lib.check(self.lib.exchange_mutate(self.table._handle, self.my_segments, self.my_counts,
-                                                    self.R, self.cap, self.P, reduce_op, self._stream()))
-        self._mark("probe received segments")
+        if len(self._chunks(pairs.shape[0])) > self.K:
+            raise ValueError("batch needs more chunks than there are lanes")
+
+        def consume(lane, lo, hi):
+            with torch.cuda.device(self.device):
+                self.lib.check(self.lib.exchange_mutate(self.table._handle, lane.my_segments, lane.my_counts,
+                                                        self.R, self.cap, self.P, reduce_op, self._stream()))
+            self._mark("probe received segments")
+
+        self._run(pairs, False, consume)
         total, mine = self._spilled()
         if total == 0:
             return None
-        return self.spill[: mine * self.slot_bytes].view(pairs.dtype).view(mine, 2).clone()
+        parts = [lane.spill[: m * self.slot_bytes].view(pairs.dtype).view(m, 2)
+                 for lane, m in zip(self.lanes, mine) if m]
+        return torch.cat(parts) if parts else pairs[:0]
 
     def lookup(self, keys, out, what):
         """what: 0 find, 1 contains. Returns (spilled keys, their source indices) or None."""
-        n = keys.shape[0]
-        self._route(keys, None, n, True)
-        with torch.cuda.device(self.device):
-            self.lib.check(self.lib.exchange_lookup(self.table._handle, self.my_segments, self.my_counts,
-                                                    self.peer_results, self.R, self.cap, self.P, self.me, what,
-                                                    self._stream()))
-        self._mark("lookup received segments")
-        self._barrier()  # every owner has stored this rank's results
-        self._mark("barrier (results landed)")
-        with torch.cuda.device(self.device):
-            self.lib.check(self.lib.exchange_unpermute(self.table._handle, self.my_results,
-                                                       _vp(self.position_local), n, _vp(out), what,
-                                                       self._stream()))
-        self._mark("unpermute")
+        if len(self._chunks(keys.shape[0])) > self.K:
+            raise ValueError("batch needs more chunks than there are lanes")
+        offsets = {}
+
+        def consume(lane, lo, hi):
+            offsets[lane.id] = lo
+            with torch.cuda.device(self.device):
+                self.lib.check(self.lib.exchange_lookup(self.table._handle, lane.my_segments, lane.my_counts,
+                                                        lane.peer_results, self.R, self.cap, self.P, self.me,
+                                                        what, self._stream()))
+            self._mark("lookup received segments")
+            self.hdl.barrier(channel=self.K + lane.id)  # every owner has stored this rank's results
+            self._mark("barrier (results landed)")
+            with torch.cuda.device(self.device):
+                self.lib.check(self.lib.exchange_unpermute(self.table._handle, lane.my_results,
+                                                           _vp(lane.position_local), hi - lo, _vp(out[lo:hi]),
+                                                           what, self._stream()))
+            self._mark("unpermute")
+
+        self._run(keys, True, consume)
         total, mine = self._spilled()
         if total == 0:
             return None
-        return (self.spill[: mine * self.key_bytes].view(keys.dtype).clone(),
-                self.spill_index[:mine].to(torch.int64))
+        spilled_keys = [lane.spill[: m * self.key_bytes].view(keys.dtype) for lane, m in zip(self.lanes, mine) if m]
+        spilled_at = [lane.spill_index[:m].to(torch.int64) + offsets.get(lane.id, 0)
+                      for lane, m in zip(self.lanes, mine) if m]
+        if not spilled_keys:
+            return keys[:0], torch.empty(0, dtype=torch.int64, device=self.device)
+        return torch.cat(spilled_keys), torch.cat(spilled_at)
 
 
 class partitioned_static_map:
     """static_map<int64,int64> sharded over the ranks of `group` by owner(key)."""
 
     def __init__(self, n_total, load_factor=0.5, *, backend, group=None, salt=DEFAULT_SALT,
-                 headroom=1.03, fused_batch=None, **table_kw):
+                 headroom=1.03, fused_batch=None, fused_lanes=None, **table_kw):
         """`fused_batch`: largest batch (elements per rank and call) the fused exchange path is sized
-        for; None keeps the all_to_all routing (also the fallback for spilled elements)."""
+        for; None keeps the all_to_all routing (also the fallback for spilled elements).
+        `fused_lanes`: chunks per batch that are software-pipelined (routing of chunk c+1 overlaps the
+        owner-side probe of chunk c); default 1 or CUCO_B200_EXCHANGE_LANES."""
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -241,7 +306,8 @@ class partitioned_static_map:
         self.table = backend.make_table(n_local, load_factor, **table_kw)
         self.fused = None
         if fused_batch:
-            self.fused = FusedExchange(self.table, fused_batch, group, backend.device, salt)
+            lanes = fused_lanes or int(os.environ.get("CUCO_B200_EXCHANGE_LANES", "1"))
+            self.fused = FusedExchange(self.table, fused_batch, group, backend.device, salt, lanes=lanes)
 
     # ---- exchange helpers ------------------------------------------------------------------------
     def _exchange_counts(self, send_counts):

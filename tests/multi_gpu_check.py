@@ -44,6 +44,9 @@ def main():
     tables = {
         "fused": partitioned.partitioned_static_map(n * world, 0.5, backend=partitioned.GpuBackend(dev),
                                                     fused_batch=n, probing="linear_probing", cg_size=1),
+        "fused, 2 pipelined lanes": partitioned.partitioned_static_map(
+            n * world, 0.5, backend=partitioned.GpuBackend(dev), fused_batch=n, fused_lanes=2,
+            probing="linear_probing", cg_size=1),
         "nccl": partitioned.partitioned_static_map(n * world, 0.5, backend=partitioned.GpuBackend(dev),
                                                    probing="linear_probing", cg_size=1),
     }
@@ -54,9 +57,23 @@ def main():
         present = t.contains(queries)
         torch.cuda.synchronize(dev)
         results[name] = (found.clone(), present.clone(), t.size())
+    for name in ("fused, 2 pipelined lanes",):
+        check(torch.equal(results[name][0], results["nccl"][0]), f"{name}: find == all_to_all find")
+        check(torch.equal(results[name][1], results["nccl"][1]), f"{name}: contains == all_to_all contains")
+        check(results[name][2] == results["nccl"][2], f"{name}: total size")
     check(torch.equal(results["fused"][0], results["nccl"][0]), "fused find == all_to_all find")
     check(torch.equal(results["fused"][1], results["nccl"][1]), "fused contains == all_to_all contains")
     check(results["fused"][2] == results["nccl"][2], f"total size {results['fused'][2]} == {results['nccl'][2]}")
+
+    # a second round through the same buffers (reuse across calls: barriers / lane hand-over)
+    more = torch.stack([keys + 7 * n, keys], dim=1).contiguous()
+    sizes = []
+    for name, t in tables.items():
+        t.insert_async(more)
+        sizes.append(t.size())
+        again = t.find(queries)
+        check(torch.equal(again, results[name][0]), f"{name}: second round leaves earlier keys intact")
+    check(len(set(sizes)) == 1, f"sizes after the second round agree: {sizes}")
 
     # the union on ONE GPU (rank 0), then every rank checks its own queries against it
     all_pairs = [torch.empty_like(pairs) for _ in range(world)]
