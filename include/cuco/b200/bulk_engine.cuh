@@ -398,8 +398,17 @@ class table_engine {
     if (n == 0) { return; }
     auto in           = unwrap(first);
     auto const engine = ref.engine();
-    auto const grid   = generic_grid(n);
-    erase_kernel<block_size><<<grid, block_size, 0, stream.get()>>>(in, n, engine);
+    using engine_t    = std::decay_t<decltype(engine)>;
+    // one key per thread, one CTA per 256 keys (random probes: the hardware scheduler balances them)
+    auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
+      cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
+    if (this->fast_path_ok(false)) {
+      erase_kernel<block_size, engine_t::sector_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, engine);
+    } else {
+      erase_kernel<block_size, engine_t::window_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, engine);
+    }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -458,8 +467,10 @@ class table_engine {
       static_cast<cuco::detail::index_type>(storage_.capacity()),
       cuco::detail::index_type{engine_type::sector_chunk_slots});
     auto const kernel = size_kernel<block_size, engine_type, size_type>;
-    auto const grid   = persistent_grid(
-      kernel, block_size, cuco::detail::int_div_ceil(chunks, cuco::detail::index_type{block_size}));
+    // persistent: (SM count x 8) CTAs stream the table, one atomic per warp at the end
+    auto const tiles = cuco::detail::int_div_ceil(chunks, cuco::detail::index_type{block_size} * 4);
+    auto const grid  = static_cast<unsigned>(std::max<cuco::detail::index_type>(
+      1, std::min<cuco::detail::index_type>(tiles, cuco::detail::index_type{cuco::detail::multiprocessor_count()} * 8)));
     kernel<<<grid, block_size, 0, stream.get()>>>(engine, counter);
     return this->read_counter(stream);
   }
@@ -554,8 +565,11 @@ class table_engine {
     if (!engine_type::pow2_slot) { return false; }
     if ((reinterpret_cast<std::uintptr_t>(storage_.data()) % 32) != 0) { return false; }
     if (mutating) {
+      // A configured erased-key sentinel does not rule the fast kernels out: a tombstone is never
+      // bit-identical to the empty slot image, so the claim CAS on it fails, the slot classifies as
+      // "available but not empty" and the key is finished by the tombstone-aware general driver
+      // (mutate_slow_path). Keys that meet no tombstone never leave the fast path.
       if (!engine_type::single_cas) { return false; }
-      if (!same_bits(erased_key_sentinel_, key_of(empty_slot_sentinel_))) { return false; }
     }
     return true;
   }

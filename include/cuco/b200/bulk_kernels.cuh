@@ -1465,12 +1465,14 @@ CUCO_KERNEL __launch_bounds__(256) void exchange_unpermute_kernel(Result const* 
 // =================================================================================================
 // erase (tombstoning) - one key per thread
 // =================================================================================================
-template <int BlockSize, typename InputIt, typename Engine>
+/// `ChunkSlots` > window size only on container-owned (padded, 32-byte aligned) storage: the walk
+/// then reads the whole sector a probe lands in, like the lookup kernels.
+template <int BlockSize, int ChunkSlots, typename InputIt, typename Engine>
 CUCO_KERNEL __launch_bounds__(BlockSize) void erase_kernel(InputIt first, index_type n, Engine engine)
 {
   for (index_type idx = cuco::detail::global_thread_id(); idx < n;
        idx += cuco::detail::grid_stride()) {
-    engine.scalar_erase(read_input(first, idx));
+    engine.template scalar_erase<ChunkSlots, load_policy::streaming>(read_input(first, idx));
   }
 }
 
@@ -1490,17 +1492,32 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void size_kernel(Engine engine, Counter
   constexpr int chunk = Engine::sector_chunk_slots;
   bool const vector_ok = (reinterpret_cast<std::uintptr_t>(table) % 32) == 0;
   if (chunk > 1 && vector_ok) {
-    // whole sectors; the allocation is padded so the last chunk may be read in full
+    // whole sectors; the allocation is padded so the last chunk may be read in full. Four
+    // independent sector loads per thread and iteration; the launch is a persistent grid so that the
+    // final count costs a few thousand atomics on the one counter, not one per warp of the table.
     index_type const chunks = (n + chunk - 1) / chunk;
-    for (index_type c = cuco::detail::global_thread_id(); c < chunks;
-         c += cuco::detail::grid_stride()) {
-      auto const raw =
-        load_chunk_bytes<chunk * Engine::slot_bytes, load_policy::readonly>(table + c * chunk);
+    constexpr int unroll    = 4;
+    for (index_type base = index_type{blockIdx.x} * (BlockSize * unroll); base < chunks;
+         base += index_type{gridDim.x} * (BlockSize * unroll)) {
+      raw_chunk<chunk * Engine::slot_bytes> raw[unroll];
 #pragma unroll
-      for (int i = 0; i < chunk; ++i) {
-        if (c * chunk + i < n) {
-          auto const& k = Engine::key_of(chunk_slot<slot_type>(raw, i));
-          mine += !(same_bits(k, empty) || same_bits(k, erased));
+      for (int u = 0; u < unroll; ++u) {
+        index_type const c = base + index_type{u} * BlockSize + threadIdx.x;
+        if (c < chunks) {
+          raw[u] = load_chunk_bytes<chunk * Engine::slot_bytes, load_policy::readonly>(table + c * chunk);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < unroll; ++u) {
+        index_type const c = base + index_type{u} * BlockSize + threadIdx.x;
+        if (c < chunks) {
+#pragma unroll
+          for (int i = 0; i < chunk; ++i) {
+            if (c * chunk + i < n) {
+              auto const& k = Engine::key_of(chunk_slot<slot_type>(raw[u], i));
+              mine += !(same_bits(k, empty) || same_bits(k, erased));
+            }
+          }
         }
       }
     }
