@@ -361,7 +361,7 @@ def main():
 
     if world > 1 or args.gpus > 1:
         from cucollections_b200 import partitioned
-        result = partitioned.bench(args, lib, args.impl)
+        result = partitioned.bench(args, lib, args.impl, clock_sampler=ClockSampler)
     else:
         result = run_single(args, lib, args.impl)
 

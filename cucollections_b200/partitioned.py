@@ -419,7 +419,7 @@ def _hbm_peak():
         return 6650.0
 
 
-def bench(args, lib, impl):
+def bench(args, lib, impl, clock_sampler=None):
     import json  # noqa: F401
     import os
 
@@ -460,8 +460,13 @@ def bench(args, lib, impl):
     assert bool((out == keys).all().item()), "partitioned find returned a wrong payload"
     dist.barrier()
     torch.cuda.synchronize(dev)
+    sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
+    if sampler is not None:
+        sampler.__enter__()
     events = [step() for _ in range(args.steps)]
     torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.__exit__(None, None, None)
     dist.barrier()
     ins = statistics.mean(a.elapsed_time(b) for a, b, _ in events)
     fnd = statistics.mean(b.elapsed_time(c) for _, b, c in events)
@@ -540,7 +545,8 @@ def bench(args, lib, impl):
         # publish + lookup + unpermute; all_to_all routing: 2 x (count + scatter) + insert (route +
         # probe when blocked) + find + scatter_by_index
         "gpu_launches": (7 if routing == "fused" else 8) * args.steps * world,
-        "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled in multi-GPU mode"]},
+        "clocks": (sampler.summary() if sampler is not None else
+                   {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}),
     }
     if table.fused is not None and table.fused.trace is not None:
         traces = [None] * world
