@@ -26,7 +26,9 @@ MAP_I64_LP1_W2 = 6
 MAP_I32_DH2_W2_MM = 7
 MAP_I32I64_LP1 = 8
 MAP_I64_DH8_X64 = 9
-NUM_KINDS = 10
+MULTISET_I32_DH4_W2 = 10
+MULTISET_I64_LP1_W2 = 11
+NUM_KINDS = 12
 
 PLUS, MIN, MAX = 0, 1, 2
 
@@ -58,6 +60,8 @@ _PROTOTYPES = {
     "cuco_b200_erase": (_int, [_vp, _vp, _i64, _vp]),
     "cuco_b200_retrieve_all": (_int, [_vp, _vp, _vp, _pi64, _vp]),
     "cuco_b200_rehash": (_int, [_vp, _i64, _vp]),
+    "cuco_b200_count": (_int, [_vp, _vp, _i64, _int, _vp, _pi64]),
+    "cuco_b200_retrieve": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _pi64, _vp]),
     "cuco_b200_insert_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "cuco_b200_find_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "cuco_b200_contains_host": (_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -1,4 +1,4 @@
-"""Host-side mirror of cuco::static_map / cuco::static_set over the C ABI, with torch tensors as the
+"""Host-side mirror of cuco::static_map / static_set / static_multiset over the C ABI, with torch tensors as the
 device buffers and torch's current CUDA stream as the `cuda::stream_ref`.
 
 Names and argument meaning follow the reference classes (include/cuco/static_map.cuh:88-986,
@@ -26,6 +26,7 @@ class _Kind:
     cg_size: int
     window_size: int
     hash: str
+    multi: bool = False  # static_multiset: equal keys are stored repeatedly
 
 
 KINDS = {
@@ -42,14 +43,16 @@ KINDS = {
               "murmurhash3_32"),
         _Kind(_cabi.MAP_I32I64_LP1, torch.int32, torch.int64, "linear_probing", 1, 1, "xxhash_32"),
         _Kind(_cabi.MAP_I64_DH8_X64, torch.int64, torch.int64, "double_hashing", 8, 1, "xxhash_64"),
+        _Kind(_cabi.MULTISET_I32_DH4_W2, torch.int32, None, "double_hashing", 4, 2, "xxhash_32", True),
+        _Kind(_cabi.MULTISET_I64_LP1_W2, torch.int64, None, "linear_probing", 1, 2, "xxhash_32", True),
     )
 }
 
 
-def find_kind(key, value, probing, cg_size, window_size, hash="xxhash_32") -> int:
+def find_kind(key, value, probing, cg_size, window_size, hash="xxhash_32", multi=False) -> int:
     for k in KINDS.values():
-        if (k.key, k.value, k.probing, k.cg_size, k.window_size, k.hash) == (
-                key, value, probing, cg_size, window_size, hash):
+        if (k.key, k.value, k.probing, k.cg_size, k.window_size, k.hash, k.multi) == (
+                key, value, probing, cg_size, window_size, hash, multi):
             return k.kind
     raise ValueError(
         f"no explicit instantiation for key={key} value={value} {probing}<{cg_size}> "
@@ -327,3 +330,54 @@ class static_set(_Table):
         n = C.c_int64()
         self._call(self._lib.retrieve_all, _ptr(keys), None, C.byref(n), self._stream())
         return keys[: n.value]
+
+    def retrieve(self, keys):
+        """static_set::retrieve (static_set.cuh:620): (probe keys that have a match, matched keys),
+        row order unspecified."""
+        k = self._check_keys(keys)
+        probed = torch.empty_like(k)
+        matched = torch.empty_like(k)
+        n = C.c_int64()
+        self._call(self._lib.retrieve, _ptr(k), k.numel(), 0, _ptr(probed), _ptr(matched),
+                   C.byref(n), self._stream())
+        return probed[: n.value], matched[: n.value]
+
+
+class static_multiset(_Table):
+    """cuco::static_multiset<Key, extent<size_t>, thread_scope_device, equal_to, Probing, ..,
+    storage<W>> (static_multiset.cuh:81-729): equal keys are stored as often as they are inserted.
+    `insert` stores every element; `count` / `retrieve` enumerate all matches of the probe keys."""
+
+    def __init__(self, capacity=None, *, n=None, load_factor=None, key_dtype=torch.int32,
+                 empty_key=-1, probing="double_hashing", cg_size=4, window_size=2,
+                 hash="xxhash_32", device=None, _library=None):
+        if (capacity is None) == (n is None):
+            raise ValueError("give either capacity or n (+ load_factor)")
+        if n is not None and load_factor is None:
+            raise ValueError("n needs a load_factor")
+        kind = find_kind(key_dtype, None, probing, cg_size, window_size, hash, multi=True)
+        super().__init__(kind, capacity if n is None else n, load_factor if n is not None else 0.0,
+                         empty_key, 0, None, device, _library)
+
+    def count(self, keys, outer=False) -> int:
+        """Total number of stored elements equal to the probe keys; `outer`: a key without matches
+        counts as one (count / count_outer, static_multiset.cuh:615,661). Synchronises."""
+        k = self._check_keys(keys)
+        out = C.c_int64()
+        self._call(self._lib.count, _ptr(k), k.numel(), 1 if outer else 0, self._stream(),
+                   C.byref(out))
+        return out.value
+
+    def retrieve(self, keys, outer=False):
+        """(probe keys, matched elements), one row per match, row order unspecified; `outer` adds
+        {key, empty key sentinel} for keys without matches (retrieve / retrieve_outer,
+        static_multiset.cuh:506,593). Sized with `count`. Synchronises."""
+        k = self._check_keys(keys)
+        rows = self.count(k, outer)
+        probed = torch.empty(rows, dtype=self.kind.key, device=self.device)
+        matched = torch.empty(rows, dtype=self.kind.key, device=self.device)
+        n = C.c_int64()
+        self._call(self._lib.retrieve, _ptr(k), k.numel(), 1 if outer else 0, _ptr(probed),
+                   _ptr(matched), C.byref(n), self._stream())
+        assert n.value == rows, (n.value, rows)
+        return probed, matched

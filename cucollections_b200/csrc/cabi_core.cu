@@ -58,7 +58,7 @@ void require(bool ok, char const* what)
 cuco_shim_factory const g_factories[CUCO_B200_NUM_KINDS] = {
   cuco_shim_make_kind_0, cuco_shim_make_kind_1, cuco_shim_make_kind_2, cuco_shim_make_kind_3,
   cuco_shim_make_kind_4, cuco_shim_make_kind_5, cuco_shim_make_kind_6, cuco_shim_make_kind_7,
-  cuco_shim_make_kind_8, cuco_shim_make_kind_9};
+  cuco_shim_make_kind_8, cuco_shim_make_kind_9, cuco_shim_make_kind_10, cuco_shim_make_kind_11};
 
 void check_launch()
 {
@@ -588,6 +588,30 @@ int cuco_b200_retrieve_all(
   return guarded([&] {
     require(t && keys_out && n_out, "NULL argument");
     *n_out = t->retrieve_all(keys_out, values_out, stream);
+  });
+}
+
+int cuco_b200_count(
+  cuco_b200_table* t, const void* keys, int64_t n, int outer, void* stream, int64_t* out)
+{
+  return guarded([&] {
+    require(t && out && n >= 0 && (keys || n == 0), "bad argument");
+    *out = t->count(keys, n, outer != 0, stream);
+  });
+}
+
+int cuco_b200_retrieve(cuco_b200_table* t,
+                       const void* keys,
+                       int64_t n,
+                       int outer,
+                       void* probe_out,
+                       void* match_out,
+                       int64_t* n_out,
+                       void* stream)
+{
+  return guarded([&] {
+    require(t && n_out && n >= 0 && ((keys && probe_out && match_out) || n == 0), "bad argument");
+    *n_out = t->retrieve(keys, n, outer != 0, probe_out, match_out, stream);
   });
 }
 

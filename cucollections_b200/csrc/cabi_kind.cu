@@ -1,10 +1,12 @@
-// One explicit instantiation of the cuco::static_map / cuco::static_set surface behind the C ABI.
+// One explicit instantiation of the cuco::static_map / static_set / static_multiset surface behind
+// the C ABI.
 // Compile with -DCUCO_SHIM_KIND=<k>; the include root on the command line decides whether this is
 // the b200-native table (-I include) or cuco's own build (-I /root/reference/include). Only the
 // public container API is used, so both compile from this one source.
 #include "cabi_table.hpp"
 
 #include <cuco/static_map.cuh>
+#include <cuco/static_multiset.cuh>
 #include <cuco/static_set.cuh>
 #include <cuco/utility/reduction_functors.cuh>
 
@@ -43,6 +45,18 @@ using set_t = cuco::static_set<K,
                                Probe,
                                cuco::cuda_allocator<K>,
                                cuco::storage<W>>;
+template <typename K, typename Probe, int W>
+using multiset_t = cuco::static_multiset<K,
+                                         cuco::extent<std::size_t>,
+                                         cuda::thread_scope_device,
+                                         eq<K>,
+                                         Probe,
+                                         cuco::cuda_allocator<K>,
+                                         cuco::storage<W>>;
+template <typename C>
+struct is_multiset : std::false_type {};
+template <typename K, typename E, cuda::thread_scope S, typename Q, typename P, typename A, typename St>
+struct is_multiset<cuco::static_multiset<K, E, S, Q, P, A, St>> : std::true_type {};
 
 #if CUCO_SHIM_KIND == 0
 using container_t = set_t<i32, cuco::double_hashing<4, cuco::default_hash_function<i32>>, 1>;
@@ -64,6 +78,10 @@ using container_t = map_t<i32, i32, cuco::double_hashing<2, cuco::murmurhash3_32
 using container_t = map_t<i32, i64, cuco::linear_probing<1, cuco::default_hash_function<i32>>, 1>;
 #elif CUCO_SHIM_KIND == 9
 using container_t = map_t<i64, i64, cuco::double_hashing<8, cuco::xxhash_64<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 10
+using container_t = multiset_t<i32, cuco::double_hashing<4, cuco::default_hash_function<i32>>, 2>;
+#elif CUCO_SHIM_KIND == 11
+using container_t = multiset_t<i64, cuco::linear_probing<1, cuco::default_hash_function<i64>>, 2>;
 #else
 #error "unknown CUCO_SHIM_KIND"
 #endif
@@ -97,7 +115,8 @@ template <typename container_t>
 class table_impl final : public cuco_b200_table {
   using key_type    = typename container_t::key_type;
   using mapped_type = typename mapped_of<container_t>::type;
-  static constexpr bool is_map = !std::is_void_v<mapped_type>;
+  static constexpr bool is_map   = !std::is_void_v<mapped_type>;
+  static constexpr bool is_multi = is_multiset<container_t>::value;
   using payload_t   = std::conditional_t<is_map, mapped_type, key_type>;  // what find() writes
   using slot_type   = typename container_t::value_type;
 
@@ -118,7 +137,12 @@ class table_impl final : public cuco_b200_table {
   {
     with_input(keys, values, n, [&](auto first, auto last) {
       if (num) {
-        *num = static_cast<i64>(c_.insert(first, last, sref(s)));
+        if constexpr (is_multi) {
+          c_.insert(first, last, sref(s));  // returns void: every element is stored
+          *num = n;
+        } else {
+          *num = static_cast<i64>(c_.insert(first, last, sref(s)));
+        }
       } else {
         c_.insert_async(first, last, sref(s));
       }
@@ -162,10 +186,14 @@ class table_impl final : public cuco_b200_table {
     (void)keys, (void)values, (void)found, (void)inserted, (void)n, (void)s;
     throw std::invalid_argument("insert_and_find: not compilable in the reference build of kind 6");
 #else
-    with_input(keys, values, n, [&](auto first, auto last) {
-      c_.insert_and_find_async(
-        first, last, static_cast<payload_t*>(found), reinterpret_cast<bool*>(inserted), sref(s));
-    });
+    if constexpr (is_multi) {
+      throw std::invalid_argument("insert_and_find is not a static_multiset operation");
+    } else {
+      with_input(keys, values, n, [&](auto first, auto last) {
+        c_.insert_and_find_async(
+          first, last, static_cast<payload_t*>(found), reinterpret_cast<bool*>(inserted), sref(s));
+      });
+    }
 #endif
   }
 
@@ -205,14 +233,20 @@ class table_impl final : public cuco_b200_table {
 
   void erase(const void* keys, i64 n, void* s) override
   {
-    auto const* k = static_cast<key_type const*>(keys);
-    c_.erase_async(k, k + n, sref(s));
+    if constexpr (is_multi) {
+      throw std::invalid_argument("erase is not a static_multiset operation");
+    } else {
+      auto const* k = static_cast<key_type const*>(keys);
+      c_.erase_async(k, k + n, sref(s));
+    }
   }
 
   i64 retrieve_all(void* keys_out, void* values_out, void* s) override
   {
     auto* k = static_cast<key_type*>(keys_out);
-    if constexpr (is_map) {
+    if constexpr (is_multi) {
+      throw std::invalid_argument("retrieve_all is not a static_multiset operation");
+    } else if constexpr (is_map) {
       auto const ends = c_.retrieve_all(k, static_cast<payload_t*>(values_out), sref(s));
       return static_cast<i64>(ends.first - k);
     } else {
@@ -222,15 +256,49 @@ class table_impl final : public cuco_b200_table {
 
   void rehash(i64 capacity, void* s) override
   {
-    if (capacity < 0) {
+    if constexpr (is_multi) {
+      throw std::invalid_argument("rehash is not a static_multiset operation");
+    } else if (capacity < 0) {
       c_.rehash(sref(s));
     } else {
       c_.rehash(static_cast<typename container_t::size_type>(capacity), sref(s));
     }
   }
 
+  i64 count(const void* keys, i64 n, bool outer, void* s) override
+  {
+    if constexpr (is_multi) {
+      auto const* k = static_cast<key_type const*>(keys);
+      if (outer) {
+        return static_cast<i64>(c_.count_outer(k, k + n, c_.key_eq(), c_.hash_function(), sref(s)));
+      }
+      return static_cast<i64>(c_.count(k, k + n, sref(s)));
+    } else {
+      throw std::invalid_argument("count is a static_multiset operation");
+    }
+  }
+
+  i64 retrieve(const void* keys, i64 n, bool outer, void* probe_out, void* match_out, void* s) override
+  {
+    auto const* k = static_cast<key_type const*>(keys);
+    auto* p       = static_cast<key_type*>(probe_out);
+    auto* m       = static_cast<key_type*>(match_out);
+    if constexpr (is_multi) {
+      if (outer) {
+        return static_cast<i64>(
+          c_.retrieve_outer(k, k + n, c_.key_eq(), c_.hash_function(), p, m, sref(s)).first - p);
+      }
+      return static_cast<i64>(c_.retrieve(k, k + n, p, m, sref(s)).first - p);
+    } else if constexpr (!is_map) {
+      if (outer) { throw std::invalid_argument("retrieve_outer is a static_multiset operation"); }
+      return static_cast<i64>(c_.retrieve(k, k + n, p, m, sref(s)).first - p);
+    } else {
+      throw std::invalid_argument("retrieve is a static_set / static_multiset operation");
+    }
+  }
+
   // ---- exchange path (no reference counterpart: our engine only) ----------------------------
-#if defined(CUCO_SHIM_REFERENCE)
+#if defined(CUCO_SHIM_REFERENCE) || (CUCO_SHIM_KIND >= 10)
   exchange_shape exchange_plan(i64, int) override { throw unsupported(); }
   void exchange_route(const void*, const void*, i64, bool, exchange_shape, int, int, std::uint64_t,
                       void* const*, void* const*, void* const*, void*, void*, void*, void*, void*,
@@ -249,7 +317,7 @@ class table_impl final : public cuco_b200_table {
   void exchange_unpermute(const void*, const void*, i64, void*, int, void*) override { throw unsupported(); }
   static std::invalid_argument unsupported()
   {
-    return std::invalid_argument("the exchange path exists in the native build only");
+    return std::invalid_argument("the exchange path exists in the native build of maps and sets only");
   }
 #else
   using engine_t = std::decay_t<decltype(std::declval<container_t&>().b200_engine())>;

@@ -29,6 +29,8 @@ struct cuco_b200_table {
   virtual void erase(const void* keys, std::int64_t n, void* stream) = 0;
   virtual std::int64_t retrieve_all(void* keys_out, void* values_out, void* stream) = 0;
   virtual void rehash(std::int64_t capacity, void* stream) = 0;
+  virtual std::int64_t count(const void* keys, std::int64_t n, bool outer, void* stream) = 0;
+  virtual std::int64_t retrieve(const void* keys, std::int64_t n, bool outer, void* probe_out, void* match_out, void* stream) = 0;
 
   // ---- exchange path of hash-partitioned tables (native build only; see include/cuco_b200.h) ----
   struct exchange_shape {
@@ -73,3 +75,5 @@ CUCO_SHIM_DECLARE_FACTORY(6);
 CUCO_SHIM_DECLARE_FACTORY(7);
 CUCO_SHIM_DECLARE_FACTORY(8);
 CUCO_SHIM_DECLARE_FACTORY(9);
+CUCO_SHIM_DECLARE_FACTORY(10);
+CUCO_SHIM_DECLARE_FACTORY(11);

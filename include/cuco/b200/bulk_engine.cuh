@@ -25,6 +25,7 @@
 #pragma once
 
 #include <cuco/b200/bulk_kernels.cuh>
+#include <cuco/b200/match_kernels.cuh>
 #include <cuco/b200/probe_engine.cuh>
 #include <cuco/detail/error.hpp>
 #include <cuco/detail/utility/cuda.hpp>
@@ -185,7 +186,8 @@ template <class Key,
           class KeyEqual,
           class ProbingScheme,
           class Allocator,
-          class Storage>
+          class Storage,
+          bool AllowsDuplicates = false>
 class table_engine {
   static_assert(sizeof(Key) <= 8, "Container does not support key types larger than 8 bytes.");
   static_assert(sizeof(Value) <= 16, "Container does not support slot types larger than 16 bytes.");
@@ -213,8 +215,9 @@ class table_engine {
   using storage_ref_type    = typename storage_type::ref_type;
   using probing_scheme_type = ProbingScheme;
   using hasher              = typename probing_scheme_type::hasher;
+  static constexpr bool allows_duplicates = AllowsDuplicates;  ///< multiset / multimap semantics
   using engine_type =
-    probe_engine<key_type, Scope, key_equal, probing_scheme_type, storage_ref_type, false>;
+    probe_engine<key_type, Scope, key_equal, probing_scheme_type, storage_ref_type, AllowsDuplicates>;
 
   static constexpr int block_size = 256;
 
@@ -454,6 +457,64 @@ class table_engine {
                  ref,
                  emit_found<typename Ref::engine_type>{empty_slot_sentinel_},
                  stream);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // all-matches queries: count / retrieve (match_kernels.cuh)
+  // ------------------------------------------------------------------------------------------
+  /// Sum over [first, last) of the number of stored elements matching each key; with `IsOuter` a key
+  /// without matches counts as one (reference open_addressing_impl.cuh:677-706). Synchronises.
+  template <bool IsOuter, typename InputIt, typename Ref>
+  [[nodiscard]] size_type count(InputIt first, InputIt last, Ref ref, cuda::stream_ref stream) const
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return 0; }
+    auto in           = unwrap(first);
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    auto* counter     = this->zeroed_counter(stream);
+    auto const grid   = generic_grid(n);
+    if (this->fast_path_ok(false)) {
+      count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+    } else {
+      count_kernel<IsOuter, block_size, engine_t::window_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+    }
+    return this->read_counter(stream);
+  }
+
+  /// For every key of [first, last) and every stored element matching it, writes the key to
+  /// `output_probe` and the element to `output_match` (same position, unspecified order); with
+  /// `IsOuter` a key without matches yields {key, empty slot sentinel}. Returns the number of rows
+  /// (reference open_addressing_impl.cuh:604-660, static_set.inl:349-373). Synchronises.
+  template <bool IsOuter, typename InputIt, typename OutputProbeIt, typename OutputMatchIt, typename Ref>
+  size_type retrieve(InputIt first,
+                     InputIt last,
+                     OutputProbeIt output_probe,
+                     OutputMatchIt output_match,
+                     Ref ref,
+                     cuda::stream_ref stream) const
+  {
+    auto const n = cuco::detail::distance(first, last);
+    if (n == 0) { return 0; }
+    auto in           = unwrap(first);
+    auto out_probe    = unwrap(output_probe);
+    auto out_match    = unwrap(output_match);
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    auto* counter     = this->zeroed_counter(stream);
+    // one CTA per round of 256 keys (like the other random-probe kernels)
+    auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
+      cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
+    if (this->fast_path_ok(false)) {
+      retrieve_kernel<IsOuter, block_size, engine_t::sector_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
+    } else {
+      retrieve_kernel<IsOuter, block_size, engine_t::window_chunk_slots>
+        <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
+    }
+    return this->read_counter(stream);
   }
 
   // ------------------------------------------------------------------------------------------

@@ -359,14 +359,20 @@ class probe_engine {
                                                     : compare_keys(probe, slot_key);
   }
 
-  /// Insert view: empty and erased slots are both AVAILABLE.
+  /// Insert view: empty and erased slots are both AVAILABLE. Tables that allow duplicates never
+  /// report EQUAL here: an occupied slot is just occupied, whatever key it holds.
   template <typename ProbeKey>
   [[nodiscard]] __device__ constexpr equal_result classify_insert(
     ProbeKey const& probe, key_type const& slot_key) const noexcept
   {
-    return (same_bits(slot_key, key_of(empty_slot_)) || same_bits(slot_key, erased_key_))
-             ? equal_result::AVAILABLE
-             : compare_keys(probe, slot_key);
+    if (same_bits(slot_key, key_of(empty_slot_)) || same_bits(slot_key, erased_key_)) {
+      return equal_result::AVAILABLE;
+    }
+    if constexpr (allows_duplicates) {
+      return equal_result::UNEQUAL;
+    } else {
+      return compare_keys(probe, slot_key);
+    }
   }
 
   [[nodiscard]] __device__ constexpr bool is_empty_key(key_type const& slot_key) const noexcept
@@ -694,18 +700,19 @@ class probe_engine {
     return erased;
   }
 
-  /// Calls `callback(slot)` for every entry matching `key`.
+  /// Calls `callback(slot content)` for every entry matching `key` (the reference hands the
+  /// callback a copy of the slot, ref_impl.cuh:1290-1316).
   template <int ChunkSlots  = window_chunk_slots,
             load_policy Policy = load_policy::plain,
             typename ProbeKey,
             typename Callback>
   __device__ void scalar_for_each(ProbeKey const& key, Callback&& callback) const noexcept
   {
-    walk<ChunkSlots, Policy>(make_cursor(key), [&](size_type index, value_type slot) {
+    walk<ChunkSlots, Policy>(make_cursor(key), [&](size_type, value_type slot) {
       auto const state = classify_lookup(key, key_of(slot));
       if (state == equal_result::EMPTY) { return true; }
       if (state == equal_result::EQUAL) {
-        callback(const_iterator{slots() + index});
+        callback(slot);
         if constexpr (!allows_duplicates) { return true; }
       }
       return false;
@@ -908,6 +915,44 @@ class probe_engine {
       base = next_base(base, step);
     }
     return cg::reduce(tile, mine, cg::plus<size_type>());
+  }
+
+  /// Per-tile for_each: every lane runs `callback(slot content)` on the matches of its own window
+  /// (up to the first empty slot of that window); `sync(tile)` runs after every probe step
+  /// (reference ref_impl.cuh:1334-1440).
+  template <typename Tile, typename ProbeKey, typename Callback, typename Sync>
+  __device__ void tile_for_each(Tile const& tile,
+                                ProbeKey const& key,
+                                Callback&& callback,
+                                Sync&& sync) const noexcept
+  {
+    auto [base, step]  = tile_plan(key);
+    auto const windows = static_cast<size_type>(storage_.window_extent());
+    while (true) {
+      size_type w = base + tile.thread_rank();
+      if (w >= windows) { w -= windows; }
+      auto const content = storage_[w];
+      bool saw_empty     = false;
+      bool saw_equal     = false;
+#pragma unroll
+      for (int i = 0; i < window_size; ++i) {
+        if (!saw_empty) {
+          auto const s = classify_lookup(key, key_of(content[i]));
+          if (s == equal_result::EMPTY) {
+            saw_empty = true;
+          } else if (s == equal_result::EQUAL) {
+            callback(content[i]);
+            saw_equal = true;
+          }
+        }
+      }
+      sync(tile);
+      if (tile.any(saw_empty)) { return; }
+      if constexpr (!allows_duplicates) {
+        if (tile.any(saw_equal)) { return; }
+      }
+      base = next_base(base, step);
+    }
   }
 
   // ----------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 // every lane.
 #pragma once
 
+#include <cuco/b200/match_kernels.cuh>
 #include <cuco/b200/probe_engine.cuh>
 #include <cuco/operator.hpp>
 
@@ -151,7 +152,7 @@ struct mixin_find : mixin_base<Ref, op::find_tag> {
 // ---- for_each ------------------------------------------------------------------------------------
 template <typename Ref, int CGSize>
 struct mixin_for_each : mixin_base<Ref, op::for_each_tag> {
-  /// Invokes `callback(slot_handle)` for every entry whose key equals `key`.
+  /// Invokes `callback(slot content)` for every entry whose key equals `key`.
   template <typename ProbeKey, typename Callback>
   __device__ void for_each(ProbeKey const& key, Callback&& callback) const noexcept
   {
@@ -159,14 +160,70 @@ struct mixin_for_each : mixin_base<Ref, op::for_each_tag> {
     this->self().engine().scalar_for_each(key, callback);
   }
 
-  /// Tile flavour: the lane that finds a match runs the callback.
+  /// Tile flavour: the lane whose window holds a match runs the callback on it.
   template <typename ProbeKey, typename Callback>
   __device__ void for_each(cooperative_groups::thread_block_tile<CGSize> const& group,
                            ProbeKey const& key,
                            Callback&& callback) const noexcept
   {
-    auto const it = this->self().engine().tile_find(group, key);
-    if (group.thread_rank() == 0 && !(it == this->self().engine().end())) { callback(it); }
+    this->self().engine().tile_for_each(group, key, callback, [](auto const&) {});
+  }
+
+  /// As above; `sync_op(group)` runs after every probe step (e.g. to flush a staging buffer).
+  template <typename ProbeKey, typename Callback, typename SyncOp>
+  __device__ void for_each(cooperative_groups::thread_block_tile<CGSize> const& group,
+                           ProbeKey const& key,
+                           Callback&& callback,
+                           SyncOp&& sync_op) const noexcept
+  {
+    this->self().engine().tile_for_each(group, key, callback, sync_op);
+  }
+};
+
+// ---- retrieve (multi-containers) -----------------------------------------------------------------
+template <typename Ref, int CGSize>
+struct mixin_retrieve : mixin_base<Ref, op::retrieve_tag> {
+  /// The whole block retrieves all matches of [first, last): rows {probe key, matched element} are
+  /// written at positions reserved from `atomic_counter` (reference ref_impl.cuh:1009-1282).
+  template <std::int32_t BlockSize,
+            class InputProbeIt,
+            class OutputProbeIt,
+            class OutputMatchIt,
+            class AtomicCounter>
+  __device__ void retrieve(cooperative_groups::thread_block const&,
+                           InputProbeIt input_probe_begin,
+                           InputProbeIt input_probe_end,
+                           OutputProbeIt output_probe,
+                           OutputMatchIt output_match,
+                           AtomicCounter& atomic_counter) const
+  {
+    run<false, BlockSize>(input_probe_begin, input_probe_end, output_probe, output_match, atomic_counter);
+  }
+
+  /// As `retrieve`; a key without matches yields {key, empty sentinel}.
+  template <std::int32_t BlockSize,
+            class InputProbeIt,
+            class OutputProbeIt,
+            class OutputMatchIt,
+            class AtomicCounter>
+  __device__ void retrieve_outer(cooperative_groups::thread_block const&,
+                                 InputProbeIt input_probe_begin,
+                                 InputProbeIt input_probe_end,
+                                 OutputProbeIt output_probe,
+                                 OutputMatchIt output_match,
+                                 AtomicCounter& atomic_counter) const
+  {
+    run<true, BlockSize>(input_probe_begin, input_probe_end, output_probe, output_match, atomic_counter);
+  }
+
+ private:
+  template <bool IsOuter, std::int32_t BlockSize, class In, class OutP, class OutM, class Counter>
+  __device__ void run(In first, In last, OutP out_probe, OutM out_match, Counter& counter) const
+  {
+    auto const& e  = this->self().engine();
+    using engine_t = cuda::std::remove_cv_t<cuda::std::remove_reference_t<decltype(e)>>;
+    block_retrieve<IsOuter, BlockSize, engine_t::window_chunk_slots, load_policy::plain>(
+      e, first, static_cast<cuco::detail::index_type>(last - first), out_probe, out_match, counter);
   }
 };
 

@@ -160,7 +160,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void for_each_key_kernel(Engine engine,
                                                                   Callback callback)
 {
   for (index_type i = cuco::detail::global_thread_id(); i < n; i += cuco::detail::grid_stride()) {
-    engine.scalar_for_each(read_input(first, i), [&](auto it) { callback(*it); });
+    engine.scalar_for_each(read_input(first, i), callback);
   }
 }
 

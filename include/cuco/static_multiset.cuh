@@ -1,14 +1,13 @@
-// cuco::static_set — fixed-capacity GPU hash set with unique keys, open addressing.
+// cuco::static_multiset — fixed-capacity GPU hash multiset (equal keys may be stored repeatedly).
 //
-// Drop-in for the reference class template (include/cuco/static_set.cuh:82-798,
-// detail/static_set/static_set.inl:35-569): same template parameters and defaults (double hashing
-// with a tile of 4, xxhash_32, one slot per window), constructors, stream-ordered bulk API and
-// `ref(ops...)`. A slot is the key itself, so claiming is a single 32/64-bit CAS; the bulk calls run
-// the sm_100a kernels of cuco/b200/bulk_kernels.cuh via cuco::b200::table_engine.
-//
-// Result semantics: insert returns the number of new keys; find writes the stored key or the empty
-// key sentinel; contains writes bool; insert_and_find writes the resident key and whether this
-// element created the entry; size counts filled slots.
+// Drop-in for the reference class template (include/cuco/static_multiset.cuh:81-729,
+// detail/static_multiset/static_multiset.inl:25-525): same template parameters and defaults (double
+// hashing with a tile of 4, xxhash_32, two slots per window), constructors, stream-ordered bulk API
+// (insert, insert_if, contains, contains_if, find, retrieve, retrieve_outer, count, count_outer,
+// size) and `ref(ops...)`. It runs on the same cuco::b200::table_engine as static_set with
+// AllowsDuplicates = true: the insert kernels claim the first free slot of the probe sequence
+// without comparing keys, `count` / `retrieve` enumerate matches up to the first empty slot
+// (cuco/b200/match_kernels.cuh).
 #pragma once
 
 #include <cuco/b200/bulk_engine.cuh>
@@ -17,7 +16,7 @@
 #include <cuco/extent.cuh>
 #include <cuco/hash_functions.cuh>
 #include <cuco/probing_scheme.cuh>
-#include <cuco/static_set_ref.cuh>
+#include <cuco/static_multiset_ref.cuh>
 #include <cuco/storage.cuh>
 #include <cuco/types.cuh>
 #include <cuco/utility/allocator.hpp>
@@ -25,7 +24,6 @@
 #include <cuco/utility/traits.hpp>
 
 #include <cuda/atomic>
-#include <cuda/std/utility>
 #include <cuda/stream_ref>
 #include <thrust/functional.h>
 
@@ -41,10 +39,10 @@ template <class Key,
           class KeyEqual           = thrust::equal_to<Key>,
           class ProbingScheme      = cuco::double_hashing<4, cuco::default_hash_function<Key>>,
           class Allocator          = cuco::cuda_allocator<Key>,
-          class Storage            = cuco::storage<1>>
-class static_set {
+          class Storage            = cuco::storage<2>>
+class static_multiset {
   using impl_type =
-    b200::table_engine<Key, Key, Extent, Scope, KeyEqual, ProbingScheme, Allocator, Storage>;
+    b200::table_engine<Key, Key, Extent, Scope, KeyEqual, ProbingScheme, Allocator, Storage, true>;
 
  public:
   static constexpr auto cg_size      = impl_type::cg_size;
@@ -62,21 +60,21 @@ class static_set {
   using hasher              = typename probing_scheme_type::hasher;
 
   template <typename... Operators>
-  using ref_type = cuco::static_set_ref<key_type,
+  using ref_type = cuco::static_multiset_ref<key_type,
                                         thread_scope,
                                         key_equal,
                                         probing_scheme_type,
                                         storage_ref_type,
                                         Operators...>;
 
-  static_set(static_set const&)            = delete;
-  static_set& operator=(static_set const&) = delete;
-  static_set(static_set&&)                 = default;
-  static_set& operator=(static_set&&)      = default;
-  ~static_set()                            = default;
+  static_multiset(static_multiset const&)            = delete;
+  static_multiset& operator=(static_multiset const&) = delete;
+  static_multiset(static_multiset&&)                 = default;
+  static_multiset& operator=(static_multiset&&)      = default;
+  ~static_multiset()                            = default;
 
-  /// Set with at least `capacity` slots (rounded up to a valid extent), all empty.
-  constexpr static_set(Extent capacity,
+  /// Multiset with at least `capacity` slots (rounded up to a valid extent), all empty.
+  constexpr static_multiset(Extent capacity,
                        empty_key<Key> empty_key_sentinel,
                        KeyEqual const& pred                = {},
                        ProbingScheme const& probing_scheme = {},
@@ -89,8 +87,8 @@ class static_set {
   {
   }
 
-  /// Set sized for `n` keys at `desired_load_factor` in (0, 1].
-  constexpr static_set(Extent n,
+  /// Multiset sized for `n` keys at `desired_load_factor` in (0, 1].
+  constexpr static_multiset(Extent n,
                        double desired_load_factor,
                        empty_key<Key> empty_key_sentinel,
                        KeyEqual const& pred                = {},
@@ -109,8 +107,8 @@ class static_set {
   {
   }
 
-  /// Set that supports erase: `erased_key_sentinel` marks tombstones and must differ from empty.
-  constexpr static_set(Extent capacity,
+  /// With an erased-key sentinel (kept for interface parity; the multiset has no erase).
+  constexpr static_multiset(Extent capacity,
                        empty_key<Key> empty_key_sentinel,
                        erased_key<Key> erased_key_sentinel,
                        KeyEqual const& pred                = {},
@@ -133,11 +131,12 @@ class static_set {
   void clear_async(cuda::stream_ref stream = {}) noexcept { impl_->clear_async(stream); }
 
   // ---- insert ----------------------------------------------------------------------------------
-  /// Inserts [first, last); returns how many keys were new. Synchronises `stream`.
+  /// Inserts every element of [first, last) (duplicates included). Synchronises `stream`.
   template <typename InputIt>
-  size_type insert(InputIt first, InputIt last, cuda::stream_ref stream = {})
+  void insert(InputIt first, InputIt last, cuda::stream_ref stream = {})
   {
-    return impl_->insert(first, last, ref(op::insert), stream);
+    impl_->insert_async(first, last, ref(op::insert), stream);
+    stream.wait();
   }
 
   template <typename InputIt>
@@ -161,43 +160,6 @@ class static_set {
                        cuda::stream_ref stream = {}) noexcept
   {
     impl_->insert_if_async(first, last, stencil, pred, ref(op::insert), stream);
-  }
-
-  /// For each element writes the key now stored for it and whether it created the entry.
-  template <typename InputIt, typename FoundIt, typename InsertedIt>
-  void insert_and_find_async(InputIt first,
-                             InputIt last,
-                             FoundIt found_begin,
-                             InsertedIt inserted_begin,
-                             cuda::stream_ref stream = {}) noexcept
-  {
-    impl_->insert_and_find_async(
-      first, last, found_begin, inserted_begin, ref(op::insert_and_find), stream);
-  }
-
-  template <typename InputIt, typename FoundIt, typename InsertedIt>
-  void insert_and_find(InputIt first,
-                       InputIt last,
-                       FoundIt found_begin,
-                       InsertedIt inserted_begin,
-                       cuda::stream_ref stream = {})
-  {
-    insert_and_find_async(first, last, found_begin, inserted_begin, stream);
-    stream.wait();
-  }
-
-  // ---- erase -----------------------------------------------------------------------------------
-  template <typename InputIt>
-  void erase(InputIt first, InputIt last, cuda::stream_ref stream = {})
-  {
-    erase_async(first, last, stream);
-    stream.wait();
-  }
-
-  template <typename InputIt>
-  void erase_async(InputIt first, InputIt last, cuda::stream_ref stream = {})
-  {
-    impl_->erase_async(first, last, ref(op::erase), stream);
   }
 
   // ---- lookups ---------------------------------------------------------------------------------
@@ -260,80 +222,102 @@ class static_set {
     impl_->find_async(first, last, output_begin, ref(op::find), stream);
   }
 
-  // ---- join probe --------------------------------------------------------------------------------
-  /// For every key k of [first, last) with a match m in the set, writes k to `output_probe` and m
-  /// to `output_match` (same position, unspecified order); returns the ends of both outputs.
-  /// Synchronises `stream`.
-  template <typename InputIt, typename OutputIt1, typename OutputIt2>
-  cuda::std::pair<OutputIt1, OutputIt2> retrieve(InputIt first,
-                                                 InputIt last,
-                                                 OutputIt1 output_probe,
-                                                 OutputIt2 output_match,
-                                                 cuda::stream_ref stream = {}) const
+  // ---- all matches: retrieve / count -----------------------------------------------------------
+  /// For every key k of [first, last) and every stored element m equal to it, writes k to
+  /// `output_probe` and m to `output_match` (same position, unspecified order). Returns the ends of
+  /// both outputs; size them with `count`. Synchronises `stream`.
+  template <class InputProbeIt, class OutputProbeIt, class OutputMatchIt>
+  std::pair<OutputProbeIt, OutputMatchIt> retrieve(InputProbeIt first,
+                                                   InputProbeIt last,
+                                                   OutputProbeIt output_probe,
+                                                   OutputMatchIt output_match,
+                                                   cuda::stream_ref stream = {}) const
   {
-    auto const rows =
-      impl_->template retrieve<false>(first, last, output_probe, output_match, ref(op::find), stream);
+    auto const rows = impl_->template retrieve<false>(
+      first, last, output_probe, output_match, ref(op::retrieve), stream);
     return {output_probe + rows, output_match + rows};
   }
 
-  /// Declared by the reference for custom probe equality / hash and documented as always throwing
-  /// (static_set.inl:376-389); kept with the same behaviour.
-  template <typename InputIt, typename OutputIt, typename ProbeEqual, typename ProbeHash>
-  OutputIt retrieve(InputIt,
-                    InputIt,
-                    OutputIt,
-                    ProbeEqual const& = ProbeEqual{},
-                    ProbeHash const&  = ProbeHash{},
-                    cuda::stream_ref  = {}) const
+  /// `retrieve` with a custom probe-key equality and hasher (heterogeneous probes).
+  template <class InputProbeIt,
+            class ProbeEqual,
+            class ProbeHash,
+            class OutputProbeIt,
+            class OutputMatchIt>
+  std::pair<OutputProbeIt, OutputMatchIt> retrieve(InputProbeIt first,
+                                                   InputProbeIt last,
+                                                   ProbeEqual const& probe_equal,
+                                                   ProbeHash const& probe_hash,
+                                                   OutputProbeIt output_probe,
+                                                   OutputMatchIt output_match,
+                                                   cuda::stream_ref stream = {}) const
   {
-    CUCO_FAIL("Unsupported code path: retrieve with custom hash/equal");
+    auto const probe_ref =
+      ref(op::retrieve).rebind_key_eq(probe_equal).rebind_hash_function(probe_hash);
+    auto const rows =
+      impl_->template retrieve<false>(first, last, output_probe, output_match, probe_ref, stream);
+    return {output_probe + rows, output_match + rows};
   }
 
-  // ---- whole-table operations ------------------------------------------------------------------
-  template <typename CallbackOp>
-  void for_each(CallbackOp&& callback_op, cuda::stream_ref stream = {}) const
+  /// As `retrieve`, but a key without matches yields the row {k, empty key sentinel}; size the
+  /// outputs with `count_outer`.
+  template <class InputProbeIt,
+            class ProbeEqual,
+            class ProbeHash,
+            class OutputProbeIt,
+            class OutputMatchIt>
+  std::pair<OutputProbeIt, OutputMatchIt> retrieve_outer(InputProbeIt first,
+                                                         InputProbeIt last,
+                                                         ProbeEqual const& probe_equal,
+                                                         ProbeHash const& probe_hash,
+                                                         OutputProbeIt output_probe,
+                                                         OutputMatchIt output_match,
+                                                         cuda::stream_ref stream = {}) const
   {
-    for_each_async(std::forward<CallbackOp>(callback_op), stream);
-    stream.wait();
+    auto const probe_ref =
+      ref(op::retrieve).rebind_key_eq(probe_equal).rebind_hash_function(probe_hash);
+    auto const rows =
+      impl_->template retrieve<true>(first, last, output_probe, output_match, probe_ref, stream);
+    return {output_probe + rows, output_match + rows};
   }
 
-  template <typename CallbackOp>
-  void for_each_async(CallbackOp&& callback_op, cuda::stream_ref stream = {}) const
+  /// Total number of stored elements matching the keys of [first, last). Synchronises `stream`.
+  template <typename InputIt>
+  size_type count(InputIt first, InputIt last, cuda::stream_ref stream = {}) const
   {
-    b200::for_each_filled_async(impl_->make_engine(), callback_op, stream);
+    return impl_->template count<false>(first, last, ref(op::count), stream);
   }
 
-  /// Copies all keys out, in unspecified order; returns the output end.
-  template <typename OutputIt>
-  OutputIt retrieve_all(OutputIt output_begin, cuda::stream_ref stream = {}) const
+  template <typename InputIt, typename ProbeKeyEqual, typename ProbeHash>
+  size_type count(InputIt first,
+                  InputIt last,
+                  ProbeKeyEqual const& probe_key_equal,
+                  ProbeHash const& probe_hash,
+                  cuda::stream_ref stream = {}) const
   {
-    return output_begin + b200::retrieve_all_elements(impl_->make_engine(), output_begin, stream);
+    return impl_->template count<false>(
+      first,
+      last,
+      ref(op::count).rebind_key_eq(probe_key_equal).rebind_hash_function(probe_hash),
+      stream);
   }
 
-  void rehash(cuda::stream_ref stream = {})
+  /// As `count`, but a key without matches counts as one.
+  template <typename InputIt, typename ProbeKeyEqual, typename ProbeHash>
+  size_type count_outer(InputIt first,
+                        InputIt last,
+                        ProbeKeyEqual const& probe_key_equal,
+                        ProbeHash const& probe_hash,
+                        cuda::stream_ref stream = {}) const
   {
-    rehash_async(stream);
-    stream.wait();
+    return impl_->template count<true>(
+      first,
+      last,
+      ref(op::count).rebind_key_eq(probe_key_equal).rebind_hash_function(probe_hash),
+      stream);
   }
 
-  void rehash(size_type capacity, cuda::stream_ref stream = {})
-  {
-    rehash_async(capacity, stream);
-    stream.wait();
-  }
-
-  void rehash_async(cuda::stream_ref stream = {})
-  {
-    b200::rehash_into(*impl_, impl_->storage_ref().window_extent(), ref(op::insert), stream);
-  }
-
-  void rehash_async(size_type capacity, cuda::stream_ref stream = {})
-  {
-    auto const extent = make_window_extent<static_set>(capacity);
-    b200::rehash_into(*impl_, extent, ref(op::insert), stream);
-  }
-
-  /// Number of keys (full scan). Synchronises `stream`.
+  /// Number of stored elements, duplicates included (full scan). Synchronises `stream`.
   [[nodiscard]] size_type size(cuda::stream_ref stream = {}) const { return impl_->size(stream); }
 
   [[nodiscard]] constexpr auto capacity() const noexcept { return impl_->capacity(); }

@@ -2,7 +2,8 @@
  *
  * The reference (NVIDIA/cuCollections) is a header-only C++ template library with no FFI; its
  * boundary for this path is the `cuco::static_map` / `cuco::static_set` class templates
- * (reference include/cuco/static_map.cuh:88-986, include/cuco/static_set.cuh:82-798), which this
+ * (reference include/cuco/static_map.cuh:88-986, include/cuco/static_set.cuh:82-798; next row:
+ * `cuco::static_multiset`, include/cuco/static_multiset.cuh:81-729), which this
  * repository re-implements under include/cuco/. This header is the plain-C view of explicit
  * instantiations of that surface, so that non-C++ hosts (ctypes, cgo, JNI, ...) and the parity /
  * benchmark harness can drive it. Every entry point names the reference member it forwards to.
@@ -43,7 +44,9 @@ enum cuco_b200_kind {
   CUCO_B200_MAP_I32_DH2_W2_MM = 7, /* static_map<int32,int32>      double_hashing<2, murmurhash3_32> w2 (reference test matrix) */
   CUCO_B200_MAP_I32I64_LP1    = 8, /* static_map<int32,int64>      linear_probing<1> w1 (padded 16 B slot: two-step claim path) */
   CUCO_B200_MAP_I64_DH8_X64   = 9, /* static_map<int64,int64>      double_hashing<8, xxhash_64> w1 (tables near 2^32 windows) */
-  CUCO_B200_NUM_KINDS         = 10
+  CUCO_B200_MULTISET_I32_DH4_W2 = 10, /* static_multiset<int32>     double_hashing<4> w2 (class default) */
+  CUCO_B200_MULTISET_I64_LP1_W2 = 11, /* static_multiset<int64>     linear_probing<1> w2 */
+  CUCO_B200_NUM_KINDS         = 12
 };
 
 /* Reduction selector for cuco_b200_insert_or_apply (cuco::reduce::plus / min / max,
@@ -145,6 +148,25 @@ int cuco_b200_erase(cuco_b200_table* t, const void* keys, int64_t n, void* strea
  * `values_out` is ignored for sets. Outputs must hold `capacity` elements. Synchronises. */
 int cuco_b200_retrieve_all(
   cuco_b200_table* t, void* keys_out, void* values_out, int64_t* n_out, void* stream);
+
+/* count / count_outer (static_multiset.cuh:615,661): *out (host) = total number of stored elements
+ * matching the n keys; outer != 0 counts a key without matches as one. Multisets only. Synchronises. */
+int cuco_b200_count(
+  cuco_b200_table* t, const void* keys, int64_t n, int outer, void* stream, int64_t* out);
+
+/* retrieve (static_set.cuh:620; static_multiset.cuh:506) / retrieve_outer (static_multiset.cuh:593):
+ * for every key and every stored element equal to it writes the key to probe_out and the element to
+ * match_out (same position, unspecified order); outer != 0 (multisets only) adds {key, empty key}
+ * for keys without matches. *n_out (host) = rows written; size the outputs with cuco_b200_count
+ * (multisets) or n (sets). Sets and multisets only. Synchronises. */
+int cuco_b200_retrieve(cuco_b200_table* t,
+                       const void* keys,
+                       int64_t n,
+                       int outer,
+                       void* probe_out,
+                       void* match_out,
+                       int64_t* n_out,
+                       void* stream);
 
 /* rehash (static_map.cuh:911,931): capacity < 0 keeps the current extent. Synchronises. */
 int cuco_b200_rehash(cuco_b200_table* t, int64_t capacity, void* stream);

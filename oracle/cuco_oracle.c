@@ -360,6 +360,7 @@ struct oracle_table {
   int64_t empty_key, empty_value, erased_key;
   int64_t* keys;
   int64_t* values; /* NULL for sets */
+  int allows_duplicates; /* static_multiset / static_multimap semantics (ref_impl.cuh:98-99) */
 };
 
 enum { UNEQUAL = 0, EQUAL = 1, EMPTY = 2, AVAILABLE = 3 }; /* equal_wrapper.cuh:28-35 */
@@ -504,6 +505,8 @@ static int classify(const oracle_table* t, int64_t probe, int64_t slot_key, int 
 {
   if (for_insert) {
     if (slot_key == t->empty_key || slot_key == t->erased_key) return AVAILABLE;
+    /* multi-containers never look for an equal key when inserting (ref_impl.cuh:389-391, 444-446) */
+    if (t->allows_duplicates) return UNEQUAL;
   } else {
     if (slot_key == t->empty_key) return EMPTY;
   }
@@ -704,6 +707,83 @@ void oracle_erase(oracle_table* t, const int64_t* keys, int64_t n)
 }
 
 /* impl.cuh:726-785 (order unspecified there; slot order here) */
+void oracle_set_allows_duplicates(oracle_table* t, int allows) { t->allows_duplicates = allows != 0; }
+
+/* ref_impl.cuh:834-892 (count) and :1046-1282 (retrieve): per probe step every lane walks its window
+ * up to the first EMPTY slot, every EQUAL slot before it is a match; the walk ends after the step
+ * in which any lane saw EMPTY. Containers without duplicates stop at the first match (:836-837).
+ * `emit` != NULL receives the slot index of every match. */
+static int64_t matches_of(const oracle_table* t, int64_t key, uint64_t* emit, int64_t emit_cap)
+{
+  probe_t p     = make_probe(t, key);
+  int64_t count = 0;
+  for (uint64_t k = 0;; k++) {
+    int saw_empty = 0;
+    for (int r = 0; r < t->cg; r++) {
+      uint64_t wdx = lane_window(t, &p, r, k);
+      for (int i = 0; i < t->w; i++) {
+        uint64_t s = wdx * (uint64_t)t->w + (uint64_t)i;
+        int st     = classify(t, key, t->keys[s], 0);
+        if (st == EMPTY) {
+          saw_empty = 1;
+          break;
+        }
+        if (st == EQUAL) {
+          if (emit && count < emit_cap) emit[count] = s;
+          count++;
+          if (!t->allows_duplicates) return count;
+        }
+      }
+    }
+    if (saw_empty) return count;
+  }
+}
+
+/* kernels.cuh:587-627 + impl.cuh:677-706: sum of matches; outer: a key without matches counts 1 */
+int64_t oracle_count(const oracle_table* t, const int64_t* keys, int64_t n, int outer)
+{
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t c = matches_of(t, narrow(keys[i], t->key_bytes), NULL, 0);
+    total += (outer && c == 0) ? 1 : c;
+  }
+  return total;
+}
+
+/* kernels.cuh:437-471, impl.cuh:604-660, static_set.inl:349-373: rows {probe key, matched slot
+ * content}; outer: {key, empty sentinel} for keys without matches. The reference leaves the row
+ * order unspecified; here rows follow input order, matches in probe order. Returns the row count;
+ * match_values_out may be NULL (sets / multisets). */
+int64_t oracle_retrieve(const oracle_table* t,
+                        const int64_t* keys,
+                        int64_t n,
+                        int outer,
+                        int64_t* probe_out,
+                        int64_t* match_keys_out,
+                        int64_t* match_values_out)
+{
+  int64_t rows = 0;
+  uint64_t* hits = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(t->capacity ? t->capacity : 1));
+  for (int64_t i = 0; i < n; i++) {
+    int64_t key = narrow(keys[i], t->key_bytes);
+    int64_t c   = matches_of(t, key, hits, (int64_t)t->capacity);
+    if (c == 0 && outer) {
+      probe_out[rows]      = key;
+      match_keys_out[rows] = t->empty_key;
+      if (match_values_out) match_values_out[rows] = t->values ? t->empty_value : 0;
+      rows++;
+    }
+    for (int64_t j = 0; j < c; j++) {
+      probe_out[rows]      = key;
+      match_keys_out[rows] = t->keys[hits[j]];
+      if (match_values_out) match_values_out[rows] = t->values ? t->values[hits[j]] : 0;
+      rows++;
+    }
+  }
+  free(hits);
+  return rows;
+}
+
 int64_t oracle_retrieve_all(const oracle_table* t, int64_t* keys_out, int64_t* values_out)
 {
   int64_t n = 0;

@@ -13,6 +13,7 @@
  *   insert/find/...   include/cuco/detail/open_addressing/open_addressing_ref_impl.cuh:374-979
  *   upserts           include/cuco/detail/static_map/static_map_ref.inl:486-620,850-1052
  *   bulk semantics    include/cuco/detail/open_addressing/kernels.cuh:64-667
+ *   count / retrieve  include/cuco/detail/open_addressing/open_addressing_ref_impl.cuh:834-892,1009-1282
  * A cooperative group of cg lanes is executed as "look at all cg windows of the step, then act",
  * which is what the ballots in the reference compute. Elements are processed in input order, so
  * where the reference says "one unspecified element wins" the oracle's answer is the first; parity
@@ -102,6 +103,21 @@ void oracle_insert_or_apply(oracle_table* t,
                             int64_t init);
 void oracle_erase(oracle_table* t, const int64_t* keys, int64_t n);
 int64_t oracle_retrieve_all(const oracle_table* t, int64_t* keys_out, int64_t* values_out);
+/* static_multiset semantics (include/cuco/static_multiset.cuh:81-729): inserts never compare keys,
+ * so equal keys are stored repeatedly. Set right after oracle_create. */
+void oracle_set_allows_duplicates(oracle_table* t, int allows);
+/* count / count_outer (open_addressing_impl.cuh:677-706): total matches of the n probe keys. */
+int64_t oracle_count(const oracle_table* t, const int64_t* keys, int64_t n, int outer);
+/* retrieve / retrieve_outer (open_addressing_impl.cuh:604-660; static_set.inl:349-373): one row
+ * {probe key, matched key[, matched payload]} per match, in input order (the reference's order is
+ * unspecified: compare sorted). Returns the number of rows; outputs sized by oracle_count. */
+int64_t oracle_retrieve(const oracle_table* t,
+                        const int64_t* keys,
+                        int64_t n,
+                        int outer,
+                        int64_t* probe_out,
+                        int64_t* match_keys_out,
+                        int64_t* match_values_out);
 /* First `len` window indices of the probe sequence of `key` as rank `rank` of a cg-wide group
  * (rank 0 of cg 1 = scalar sequence); for tests/utility/probing_scheme_test.cu style checks. */
 void oracle_probe_sequence(const oracle_table* t, int64_t key, int rank, int64_t* out, int len);

@@ -66,6 +66,9 @@ def lib() -> C.CDLL:
         L.oracle_erase.restype, L.oracle_erase.argtypes = None, [vp, vp, i64]
         L.oracle_retrieve_all.restype, L.oracle_retrieve_all.argtypes = i64, [vp, vp, vp]
         L.oracle_probe_sequence.restype, L.oracle_probe_sequence.argtypes = None, [vp, i64, i, vp, i]
+        L.oracle_set_allows_duplicates.restype, L.oracle_set_allows_duplicates.argtypes = None, [vp, i]
+        L.oracle_count.restype, L.oracle_count.argtypes = i64, [vp, vp, i64, i]
+        L.oracle_retrieve.restype, L.oracle_retrieve.argtypes = i64, [vp, vp, i64, i, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -119,14 +122,17 @@ KIND_GEOMETRY = {
     7: (4, 4, 2, 2, DOUBLE, MURMUR3_32),
     8: (4, 8, 1, 1, LINEAR, XXHASH32),
     9: (8, 8, 8, 1, DOUBLE, XXHASH64),
+    10: (4, 0, 4, 2, DOUBLE, XXHASH32),
+    11: (8, 0, 1, 2, LINEAR, XXHASH32),
 }
+MULTI_KINDS = {10, 11}  # static_multiset instantiations: equal keys are stored repeatedly
 
 
 class Table:
     """Sequential CPU table with the reference's semantics. Arrays in and out are numpy int64."""
 
     def __init__(self, key_bytes, value_bytes, cg, w, probing, hash, size, load_factor=0.0,
-                 empty_key=-1, empty_value=-1, erased_key=None):
+                 empty_key=-1, empty_value=-1, erased_key=None, allows_duplicates=False):
         self.is_map = value_bytes != 0
         self._h = lib().oracle_create(key_bytes, value_bytes, cg, w, probing, hash, int(size),
                                       float(load_factor), int(empty_key), int(empty_value),
@@ -134,10 +140,13 @@ class Table:
                                       0 if erased_key is None else int(erased_key))
         if not self._h:
             raise ValueError("oracle_create rejected the arguments")
+        if allows_duplicates:
+            lib().oracle_set_allows_duplicates(self._h, 1)
 
     @classmethod
     def for_kind(cls, kind, size, load_factor=0.0, empty_key=-1, empty_value=-1, erased_key=None):
-        return cls(*KIND_GEOMETRY[kind], size, load_factor, empty_key, empty_value, erased_key)
+        return cls(*KIND_GEOMETRY[kind], size, load_factor, empty_key, empty_value, erased_key,
+                   allows_duplicates=kind in MULTI_KINDS)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -207,6 +216,21 @@ class Table:
         v = np.empty(cap, dtype=np.int64)
         n = int(lib().oracle_retrieve_all(self._h, _p(k), _p(v)))
         return (k[:n], v[:n]) if self.is_map else k[:n]
+
+    def count(self, keys, outer=False):
+        k = _i64(keys)
+        return int(lib().oracle_count(self._h, _p(k), k.size, 1 if outer else 0))
+
+    def retrieve(self, keys, outer=False):
+        """(probe keys, matched keys[, matched payloads]) in input order / probe order."""
+        k = _i64(keys)
+        rows = self.count(k, outer)
+        probe = np.empty(rows, dtype=np.int64)
+        mk = np.empty(rows, dtype=np.int64)
+        mv = np.empty(rows, dtype=np.int64) if self.is_map else None
+        n = int(lib().oracle_retrieve(self._h, _p(k), k.size, 1 if outer else 0, _p(probe), _p(mk), _p(mv)))
+        assert n == rows
+        return (probe, mk, mv) if self.is_map else (probe, mk)
 
     def probe_sequence(self, key, rank=0, length=8):
         out = np.empty(length, dtype=np.int64)

@@ -3,11 +3,14 @@
 // only the public cuco:: API, in the ways the reference's own tests and examples do:
 //   tests/static_map/{unique_sequence,insert_and_find,insert_or_assign,insert_or_apply,
 //                     heterogeneous_lookup,key_sentinel,shared_memory,stream,for_each,erase}_test.cu
-//   tests/static_set/{unique_sequence,insert_and_find,shared_memory,heterogeneous_lookup}_test.cu
+//   tests/static_set/{unique_sequence,insert_and_find,shared_memory,heterogeneous_lookup,
+//                     retrieve}_test.cu
+//   tests/static_multiset/{insert,contains,find,count,custom_count,retrieve,for_each}_test.cu
 //   tests/utility/probing_scheme_test.cu, examples/static_map/device_ref_example.cu,
 //   examples/static_set/device_ref_example.cu, examples/static_map/count_by_key_example.cu
 // Prints one line per check and a JSON summary; exit code 0 iff everything passed.
 #include <cuco/static_map.cuh>
+#include <cuco/static_multiset.cuh>
 #include <cuco/static_set.cuh>
 #include <cuco/utility/reduction_functors.cuh>
 
@@ -20,7 +23,9 @@
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/iterator/zip_iterator.h>
 #include <thrust/logical.h>
+#include <thrust/random.h>
 #include <thrust/sequence.h>
+#include <thrust/shuffle.h>
 #include <thrust/sort.h>
 
 #include <cuda/functional>
@@ -662,6 +667,217 @@ static void probing_suite()
   CHECK(thrust::equal(a.begin(), a.end(), b.begin()));
 }
 
+// ------------------------------------------------------------------------------------------------
+// join probe of a set: static_set::retrieve (tests/static_set/retrieve_test.cu)
+// ------------------------------------------------------------------------------------------------
+template <typename Key, typename Probe>
+static void set_retrieve_suite(char const* label)
+{
+  std::printf("# static_set::retrieve, %s\n", label);
+  constexpr std::size_t n = 400;
+  auto set = cuco::static_set{n, 1.0, cuco::empty_key<Key>{-1}, {}, Probe{}};
+  thrust::device_vector<Key> probed(n), matched(n);
+  auto const iter = thrust::counting_iterator<Key>{0};
+  {
+    auto const ends = set.retrieve(iter, iter + n, probed.begin(), matched.begin());
+    CHECK(ends.first - probed.begin() == 0);
+    CHECK(ends.second - matched.begin() == 0);
+  }
+  set.insert(iter, iter + n);
+  {
+    // twice as many probes as keys: the second half has no match and must not produce rows
+    auto const ends = set.retrieve(iter, iter + 2 * n, probed.begin(), matched.begin());
+    CHECK(ends.first - probed.begin() == static_cast<std::ptrdiff_t>(n));
+    CHECK(ends.second - matched.begin() == static_cast<std::ptrdiff_t>(n));
+    thrust::sort(probed.begin(), probed.end());
+    thrust::sort(matched.begin(), matched.end());
+    CHECK(thrust::equal(probed.begin(), probed.end(), iter));
+    CHECK(thrust::equal(matched.begin(), matched.end(), iter));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// static_multiset (tests/static_multiset/*.cu)
+// ------------------------------------------------------------------------------------------------
+template <typename Key>
+struct divide_by {
+  Key divisor;
+  __host__ __device__ Key operator()(Key i) const { return i / divisor; }
+};
+
+template <typename Ref, typename KeyIt>
+__global__ void multiset_ref_scalar_kernel(Ref ref, KeyIt keys, std::size_t n, std::size_t multiplicity, int* errors)
+{
+  for (std::size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    auto const key      = *(keys + i);
+    std::size_t matches = 0;
+    ref.for_each(key, [&](auto const slot) {
+      if (ref.key_eq()(key, slot)) { ++matches; }
+    });
+    if (matches != multiplicity) { atomicAdd(errors, 1); }
+    if (static_cast<std::size_t>(ref.count(key)) != multiplicity) { atomicAdd(errors, 1); }
+    if (ref.contains(key) != (multiplicity != 0)) { atomicAdd(errors, 1); }
+  }
+}
+
+template <bool Synced, typename Ref, typename KeyIt>
+__global__ void multiset_ref_tile_kernel(Ref ref, KeyIt keys, std::size_t n, std::size_t multiplicity, int* errors)
+{
+  constexpr int cgs = Ref::cg_size;
+  auto const tile   = cg::tiled_partition<cgs>(cg::this_thread_block());
+  for (std::size_t i = (blockIdx.x * blockDim.x + threadIdx.x) / cgs; i < n;
+       i += (gridDim.x * blockDim.x) / cgs) {
+    auto const key     = *(keys + i);
+    std::size_t mine   = 0;
+    auto const on_slot = [&](auto const slot) {
+      if (ref.key_eq()(key, slot)) { ++mine; }
+    };
+    if constexpr (Synced) {
+      ref.for_each(tile, key, on_slot, [](auto const& group) { group.sync(); });
+    } else {
+      ref.for_each(tile, key, on_slot);
+    }
+    auto const total = cg::reduce(tile, mine, cg::plus<std::size_t>());
+    auto const count = ref.count(tile, key);
+    if (tile.thread_rank() == 0) {
+      if (total != multiplicity) { atomicAdd(errors, 1); }
+      if (static_cast<std::size_t>(count) != multiplicity) { atomicAdd(errors, 1); }
+    }
+  }
+}
+
+template <int BlockSize, typename Ref, typename KeyIt, typename Key, typename Counter>
+__global__ void multiset_ref_retrieve_kernel(
+  Ref ref, KeyIt keys, std::size_t n, Key* probed, Key* matched, Counter* counter, bool outer)
+{
+  auto const block = cg::this_thread_block();
+  if (outer) {
+    ref.template retrieve_outer<BlockSize>(block, keys, keys + n, probed, matched, *counter);
+  } else {
+    ref.template retrieve<BlockSize>(block, keys, keys + n, probed, matched, *counter);
+  }
+}
+
+template <typename Key, typename Probe>
+static void multiset_suite(char const* label)
+{
+  std::printf("# static_multiset, %s\n", label);
+  using set_type = cuco::static_multiset<Key,
+                                         cuco::extent<std::size_t>,
+                                         cuda::thread_scope_device,
+                                         thrust::equal_to<Key>,
+                                         Probe,
+                                         cuco::cuda_allocator<Key>,
+                                         cuco::storage<2>>;
+  constexpr std::size_t unique = 400, multiplicity = 5, n = unique * multiplicity;
+  auto set = set_type{cuco::extent<std::size_t>{2 * n}, cuco::empty_key<Key>{-1}};
+  auto const iter = thrust::counting_iterator<Key>{0};
+
+  // count / contains / retrieve on the empty container
+  CHECK(set.size() == 0);
+  CHECK(set.count(iter, iter + n) == 0);
+  thrust::device_vector<bool> present(2 * n);
+  set.contains(iter, iter + n, present.begin());
+  CHECK(none_true(present.begin(), present.begin() + n));
+
+  // n unique keys: count == n, every key contained and found (insert / contains / find tests)
+  set.insert(iter, iter + n);
+  CHECK(set.size() == n);
+  CHECK(set.count(iter, iter + n) == n);
+  set.contains(iter, iter + 2 * n, present.begin());
+  CHECK(all_true(present.begin(), present.begin() + n));
+  CHECK(none_true(present.begin() + n, present.end()));
+  thrust::device_vector<Key> found(2 * n);
+  set.find(iter, iter + 2 * n, found.begin());
+  CHECK(thrust::equal(found.begin(), found.begin() + n, iter));
+  CHECK(thrust::count(found.begin() + n, found.end(), Key(-1)) == static_cast<std::ptrdiff_t>(n));
+  // every query repeated three times
+  auto const thirds = thrust::make_transform_iterator(iter, divide_by<Key>{3});
+  CHECK(set.count(thirds, thirds + 3 * n) == 3 * n);
+
+  // multiplicity: each of `unique` keys stored `multiplicity` times, shuffled input
+  set.clear();
+  thrust::device_vector<Key> input(n);
+  thrust::transform(iter, iter + n, input.begin(), divide_by<Key>{static_cast<Key>(multiplicity)});
+  thrust::shuffle(input.begin(), input.end(), thrust::default_random_engine{7});
+  thrust::device_vector<std::uint8_t> stencil(n);
+  thrust::transform(iter, iter + n, stencil.begin(), is_even{});
+  CHECK(set.insert_if(input.begin(), input.end(), stencil.begin(), is_even{}) == n / 2);
+  CHECK(set.size() == n / 2);
+  set.clear();
+  set.insert(input.begin(), input.end());
+  CHECK(set.size() == n);
+  CHECK(set.count(iter, iter + unique) == n);
+  CHECK(set.count(iter, iter + 2 * unique) == n);
+  CHECK(set.count_outer(iter, iter + 2 * unique, set.key_eq(), set.hash_function()) == n + unique);
+  {
+    thrust::device_vector<Key> probed(n * multiplicity), matched(n * multiplicity);
+    // probing with the stored stream itself: every element matches `multiplicity` elements
+    auto const ends = set.retrieve(input.begin(), input.end(), probed.begin(), matched.begin());
+    CHECK(ends.first - probed.begin() == static_cast<std::ptrdiff_t>(n * multiplicity));
+    CHECK(ends.second - matched.begin() == static_cast<std::ptrdiff_t>(n * multiplicity));
+    CHECK(thrust::equal(probed.begin(), probed.end(), matched.begin()));
+    thrust::sort(probed.begin(), probed.end());
+    auto const expected =
+      thrust::make_transform_iterator(iter, divide_by<Key>{static_cast<Key>(multiplicity * multiplicity)});
+    CHECK(thrust::equal(probed.begin(), probed.end(), expected));
+  }
+  {
+    // outer retrieve over [0, 2 * unique): the upper half has no match and yields the sentinel
+    thrust::device_vector<Key> probed(n + unique), matched(n + unique);
+    auto const ends = set.retrieve_outer(
+      iter, iter + 2 * unique, set.key_eq(), set.hash_function(), probed.begin(), matched.begin());
+    CHECK(ends.first - probed.begin() == static_cast<std::ptrdiff_t>(n + unique));
+    thrust::sort_by_key(probed.begin(), probed.end(), matched.begin());
+    CHECK(thrust::equal(probed.begin(), probed.begin() + n, matched.begin()));
+    CHECK(thrust::equal(probed.begin() + n, probed.end(), iter + unique));
+    CHECK(thrust::count(matched.begin() + n, matched.end(), Key(-1)) == static_cast<std::ptrdiff_t>(unique));
+  }
+
+  // device refs: for_each / count / contains per thread or per tile, block-wide retrieve
+  thrust::device_vector<int> errors(1, 0);
+  if constexpr (set_type::cg_size == 1) {
+    multiset_ref_scalar_kernel<<<8, 128>>>(
+      set.ref(cuco::for_each, cuco::count, cuco::contains), iter, unique, multiplicity, errors.data().get());
+    multiset_ref_scalar_kernel<<<8, 128>>>(
+      set.ref(cuco::for_each, cuco::count, cuco::contains), iter + unique, unique, std::size_t{0}, errors.data().get());
+  } else {
+    multiset_ref_tile_kernel<false><<<8, 128>>>(
+      set.ref(cuco::for_each, cuco::count), iter, unique, multiplicity, errors.data().get());
+    multiset_ref_tile_kernel<true><<<8, 128>>>(
+      set.ref(cuco::for_each, cuco::count), iter, unique, multiplicity, errors.data().get());
+    multiset_ref_tile_kernel<false><<<8, 128>>>(
+      set.ref(cuco::for_each, cuco::count), iter + unique, unique, std::size_t{0}, errors.data().get());
+  }
+  cudaDeviceSynchronize();
+  CHECK(errors[0] == 0);
+  {
+    using counter_type = cuda::atomic<typename set_type::size_type, cuda::thread_scope_device>;
+    thrust::device_vector<Key> probed(n + unique), matched(n + unique);
+    counter_type* counter{};
+    cudaMalloc(&counter, sizeof(counter_type));
+    for (bool outer : {false, true}) {
+      cudaMemset(counter, 0, sizeof(counter_type));
+      multiset_ref_retrieve_kernel<128><<<1, 128>>>(set.ref(cuco::retrieve),
+                                                   iter,
+                                                   2 * unique,
+                                                   probed.data().get(),
+                                                   matched.data().get(),
+                                                   counter,
+                                                   outer);
+      typename set_type::size_type rows{};
+      cudaMemcpy(&rows, counter, sizeof(rows), cudaMemcpyDeviceToHost);
+      CHECK(rows == (outer ? n + unique : n));
+      thrust::sort_by_key(probed.begin(), probed.begin() + rows, matched.begin());
+      CHECK(thrust::equal(probed.begin(), probed.begin() + n, matched.begin()));
+      auto const expected =
+        thrust::make_transform_iterator(iter, divide_by<Key>{static_cast<Key>(multiplicity)});
+      CHECK(thrust::equal(probed.begin(), probed.begin() + n, expected));
+    }
+    cudaFree(counter);
+  }
+}
+
 int main()
 {
   bulk_api_suite<std::int64_t, std::int64_t, cuco::linear_probing<1, cuco::default_hash_function<std::int64_t>>, 1>(
@@ -687,6 +903,18 @@ int main()
   key_sentinel_suite();
   duplicate_and_set_suite();
   probing_suite();
+  set_retrieve_suite<std::int32_t, cuco::double_hashing<2, cuco::default_hash_function<std::int32_t>>>(
+    "int32 double_hashing<2>");
+  set_retrieve_suite<std::int64_t, cuco::linear_probing<1, cuco::default_hash_function<std::int64_t>>>(
+    "int64 linear_probing<1>");
+  multiset_suite<std::int32_t, cuco::double_hashing<4, cuco::default_hash_function<std::int32_t>>>(
+    "int32 double_hashing<4> storage<2> (class defaults)");
+  multiset_suite<std::int64_t, cuco::linear_probing<1, cuco::default_hash_function<std::int64_t>>>(
+    "int64 linear_probing<1> storage<2>");
+  multiset_suite<std::int64_t, cuco::double_hashing<2, cuco::default_hash_function<std::int64_t>>>(
+    "int64 double_hashing<2> storage<2>");
+  multiset_suite<std::int32_t, cuco::linear_probing<1, cuco::default_hash_function<std::int32_t>>>(
+    "int32 linear_probing<1> storage<2>");
   cudaDeviceSynchronize();
   bool const cuda_ok = cudaGetLastError() == cudaSuccess;
   report(cuda_ok, "no CUDA error at exit");

@@ -130,7 +130,7 @@ def test_probe_sequences_scalar_equals_cg1():
     assert (base[1] - base[0]) % 4 == 0
 
 
-@pytest.mark.parametrize("kind", list(o.KIND_GEOMETRY))
+@pytest.mark.parametrize("kind", [k for k in o.KIND_GEOMETRY if k not in o.MULTI_KINDS])
 def test_table_semantics_against_python_dict(kind):
     """Set/map semantics of tests/static_{map,set}/unique_sequence_test.cu, duplicate_keys_test.cu,
     insert_and_find_test.cu, insert_or_assign_test.cu on every geometry."""
