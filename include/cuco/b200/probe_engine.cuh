@@ -892,7 +892,9 @@ class probe_engine {
     }
   }
 
-  /// Per-tile count: every lane counts matches in its window; result is the tile-wide sum.
+  /// Per-tile count: every lane counts the matches in its own windows and returns THAT number, like
+  /// the reference ("occurrences found by the current thread", ref_impl.cuh:860-892); callers sum
+  /// over the tile.
   template <typename Tile, typename ProbeKey>
   [[nodiscard]] __device__ size_type tile_count(Tile const& tile,
                                                 ProbeKey const& key) const noexcept
@@ -914,7 +916,7 @@ class probe_engine {
       if (tile.any(saw_empty)) { break; }
       base = next_base(base, step);
     }
-    return cg::reduce(tile, mine, cg::plus<size_type>());
+    return mine;
   }
 
   /// Per-tile for_each: every lane runs `callback(slot content)` on the matches of its own window

@@ -122,6 +122,7 @@ struct mixin_count : mixin_base<Ref, op::count_tag> {
     return this->self().engine().scalar_count(key);
   }
 
+  /// Matches found by the calling lane in its own windows; sum over the tile for the key's count.
   template <typename ProbeKey>
   [[nodiscard]] __device__ auto count(cooperative_groups::thread_block_tile<CGSize> const& group,
                                       ProbeKey const& key) const noexcept

@@ -738,10 +738,12 @@ __global__ void multiset_ref_tile_kernel(Ref ref, KeyIt keys, std::size_t n, std
       ref.for_each(tile, key, on_slot);
     }
     auto const total = cg::reduce(tile, mine, cg::plus<std::size_t>());
-    auto const count = ref.count(tile, key);
+    // the tile overload returns the matches seen by the calling lane
+    auto const count =
+      cg::reduce(tile, static_cast<std::size_t>(ref.count(tile, key)), cg::plus<std::size_t>());
     if (tile.thread_rank() == 0) {
       if (total != multiplicity) { atomicAdd(errors, 1); }
-      if (static_cast<std::size_t>(count) != multiplicity) { atomicAdd(errors, 1); }
+      if (count != multiplicity) { atomicAdd(errors, 1); }
     }
   }
 }

@@ -71,8 +71,9 @@ def test_multiset_matches_oracle(kind, generic, native_lib):
     keys = skewed_keys(n, n // 4, 11)
     queries = np.concatenate([np.arange(0, n // 4, dtype=np.int64), np.arange(n, n + 3000, dtype=np.int64)])
     for lf in (0.5, 0.9):
-        t = make(kind, native_lib, n=n, load_factor=lf)
-        ref = oracle.Table.for_kind(kind, n, lf)
+        # sized for 2n elements: the stream is inserted twice below (overfilling never terminates)
+        t = make(kind, native_lib, n=2 * n, load_factor=lf)
+        ref = oracle.Table.for_kind(kind, 2 * n, lf)
         assert t.capacity() == ref.capacity()
         assert t.count(dev(queries, k.key)) == 0
         assert t.insert(dev(keys, k.key)) == ref.insert(keys) == n   # every element is stored

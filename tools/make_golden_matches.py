@@ -105,7 +105,7 @@ def run_scenario(kind, b):
         caps.append(b.make(capacity=c).capacity())
     out[tag + "capacities"] = np.asarray(caps, dtype=np.int64)
 
-    t = b.make(n=N, load_factor=0.7)
+    t = b.make(n=2 * N, load_factor=0.7)  # insert_if (~N/2) + insert (N) elements stay below capacity
     out[tag + "insert_if_new"] = np.int64(t.insert_if(b.keys(a), b.stencil(stencil)))
     out[tag + "size_after_insert_if"] = np.int64(t.size())
     out[tag + "insert_new"] = np.int64(t.insert(b.keys(a)))
