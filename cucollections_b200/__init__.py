@@ -8,7 +8,7 @@ hand-written sm_100a kernels. There is no CPU fallback.
 """
 from . import _cabi
 from ._cabi import CucoError, Library, native
-from .containers import KINDS, find_kind, static_map, static_multiset, static_set
+from .containers import KINDS, find_kind, static_map, static_multimap, static_multiset, static_set
 
-__all__ = ["CucoError", "Library", "native", "KINDS", "find_kind", "static_map", "static_multiset", "static_set",
+__all__ = ["CucoError", "Library", "native", "KINDS", "find_kind", "static_map", "static_multimap", "static_multiset", "static_set",
            "_cabi"]

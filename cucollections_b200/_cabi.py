@@ -28,7 +28,8 @@ MAP_I32I64_LP1 = 8
 MAP_I64_DH8_X64 = 9
 MULTISET_I32_DH4_W2 = 10
 MULTISET_I64_LP1_W2 = 11
-NUM_KINDS = 12
+MULTIMAP_I64_LP4 = 12
+NUM_KINDS = 13
 
 PLUS, MIN, MAX = 0, 1, 2
 

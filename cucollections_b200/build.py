@@ -24,7 +24,7 @@ CSRC = ROOT / "cucollections_b200" / "csrc"
 NATIVE_LIB = ROOT / "cucollections_b200" / "libcuco_b200.so"
 REF_LIB = ROOT / "oracle" / "_ref" / "libcuco_ref.so"
 REFERENCE_INCLUDE = Path("/root/reference/include")
-NUM_KINDS = 12
+NUM_KINDS = 13
 # kinds whose launch parameters can be switched at run time (bench / sweep configurations)
 TUNABLE_KINDS = {0, 1, 2, 3}
 

@@ -45,6 +45,7 @@ KINDS = {
         _Kind(_cabi.MAP_I64_DH8_X64, torch.int64, torch.int64, "double_hashing", 8, 1, "xxhash_64"),
         _Kind(_cabi.MULTISET_I32_DH4_W2, torch.int32, None, "double_hashing", 4, 2, "xxhash_32", True),
         _Kind(_cabi.MULTISET_I64_LP1_W2, torch.int64, None, "linear_probing", 1, 2, "xxhash_32", True),
+        _Kind(_cabi.MULTIMAP_I64_LP4, torch.int64, torch.int64, "linear_probing", 4, 1, "xxhash_32", True),
     )
 }
 
@@ -341,6 +342,30 @@ class static_set(_Table):
         self._call(self._lib.retrieve, _ptr(k), k.numel(), 0, _ptr(probed), _ptr(matched),
                    C.byref(n), self._stream())
         return probed[: n.value], matched[: n.value]
+
+
+class static_multimap(_Table):
+    """cuco::experimental::static_multimap<Key, T, ...> (static_multimap.cuh:45-549): a key may map to
+    any number of payloads. Bulk API of the reference class: `insert[_async]`, `insert_if`,
+    `contains`, `contains_if`, `count`."""
+
+    def __init__(self, capacity=None, *, n=None, load_factor=None, key_dtype=torch.int64,
+                 value_dtype=torch.int64, empty_key=-1, empty_value=-1, probing="linear_probing",
+                 cg_size=4, window_size=1, hash="xxhash_32", device=None, _library=None):
+        if (capacity is None) == (n is None):
+            raise ValueError("give either capacity or n (+ load_factor)")
+        if n is not None and load_factor is None:
+            raise ValueError("n needs a load_factor")
+        kind = find_kind(key_dtype, value_dtype, probing, cg_size, window_size, hash, multi=True)
+        super().__init__(kind, capacity if n is None else n, load_factor if n is not None else 0.0,
+                         empty_key, empty_value, None, device, _library)
+
+    def count(self, keys) -> int:
+        """Total number of stored pairs whose key equals a probe key. Synchronises."""
+        k = self._check_keys(keys)
+        out = C.c_int64()
+        self._call(self._lib.count, _ptr(k), k.numel(), 0, self._stream(), C.byref(out))
+        return out.value
 
 
 class static_multiset(_Table):

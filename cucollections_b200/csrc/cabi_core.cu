@@ -58,7 +58,8 @@ void require(bool ok, char const* what)
 cuco_shim_factory const g_factories[CUCO_B200_NUM_KINDS] = {
   cuco_shim_make_kind_0, cuco_shim_make_kind_1, cuco_shim_make_kind_2, cuco_shim_make_kind_3,
   cuco_shim_make_kind_4, cuco_shim_make_kind_5, cuco_shim_make_kind_6, cuco_shim_make_kind_7,
-  cuco_shim_make_kind_8, cuco_shim_make_kind_9, cuco_shim_make_kind_10, cuco_shim_make_kind_11};
+  cuco_shim_make_kind_8, cuco_shim_make_kind_9, cuco_shim_make_kind_10, cuco_shim_make_kind_11,
+  cuco_shim_make_kind_12};
 
 void check_launch()
 {

@@ -6,6 +6,7 @@
 #include "cabi_table.hpp"
 
 #include <cuco/static_map.cuh>
+#include <cuco/static_multimap.cuh>
 #include <cuco/static_multiset.cuh>
 #include <cuco/static_set.cuh>
 #include <cuco/utility/reduction_functors.cuh>
@@ -53,6 +54,19 @@ using multiset_t = cuco::static_multiset<K,
                                          Probe,
                                          cuco::cuda_allocator<K>,
                                          cuco::storage<W>>;
+template <typename K, typename V, typename Probe, int W>
+using multimap_t = cuco::experimental::static_multimap<K,
+                                                       V,
+                                                       cuco::extent<std::size_t>,
+                                                       cuda::thread_scope_device,
+                                                       eq<K>,
+                                                       Probe,
+                                                       cuco::cuda_allocator<cuco::pair<K, V>>,
+                                                       cuco::storage<W>>;
+template <typename C>
+struct is_multimap : std::false_type {};
+template <typename K, typename V, typename E, cuda::thread_scope S, typename Q, typename P, typename A, typename St>
+struct is_multimap<cuco::experimental::static_multimap<K, V, E, S, Q, P, A, St>> : std::true_type {};
 template <typename C>
 struct is_multiset : std::false_type {};
 template <typename K, typename E, cuda::thread_scope S, typename Q, typename P, typename A, typename St>
@@ -82,6 +96,8 @@ using container_t = map_t<i64, i64, cuco::double_hashing<8, cuco::xxhash_64<i64>
 using container_t = multiset_t<i32, cuco::double_hashing<4, cuco::default_hash_function<i32>>, 2>;
 #elif CUCO_SHIM_KIND == 11
 using container_t = multiset_t<i64, cuco::linear_probing<1, cuco::default_hash_function<i64>>, 2>;
+#elif CUCO_SHIM_KIND == 12
+using container_t = multimap_t<i64, i64, cuco::linear_probing<4, cuco::default_hash_function<i64>>, 1>;
 #else
 #error "unknown CUCO_SHIM_KIND"
 #endif
@@ -116,7 +132,8 @@ class table_impl final : public cuco_b200_table {
   using key_type    = typename container_t::key_type;
   using mapped_type = typename mapped_of<container_t>::type;
   static constexpr bool is_map   = !std::is_void_v<mapped_type>;
-  static constexpr bool is_multi = is_multiset<container_t>::value;
+  static constexpr bool is_multimap_v = is_multimap<container_t>::value;
+  static constexpr bool is_multi      = is_multiset<container_t>::value || is_multimap_v;  // duplicates
   using payload_t   = std::conditional_t<is_map, mapped_type, key_type>;  // what find() writes
   using slot_type   = typename container_t::value_type;
 
@@ -130,7 +147,16 @@ class table_impl final : public cuco_b200_table {
   int key_bytes() const override { return sizeof(key_type); }
   int value_bytes() const override { return is_map ? sizeof(payload_t) : 0; }
   i64 capacity() const override { return static_cast<i64>(c_.capacity()); }
-  i64 size(void* s) override { return static_cast<i64>(c_.size(sref(s))); }
+  i64 size(void* s) override
+  {
+    if constexpr (is_multimap_v) {
+      // the reference class has no size(); count over the whole key domain is not expressible either
+      (void)s;
+      throw std::invalid_argument("size is not an experimental::static_multimap operation");
+    } else {
+      return static_cast<i64>(c_.size(sref(s)));
+    }
+  }
   void clear(void* s) override { c_.clear_async(sref(s)); }
 
   void insert(const void* keys, const void* values, i64 n, void* s, i64* num) override
@@ -162,8 +188,12 @@ class table_impl final : public cuco_b200_table {
 
   void find(const void* keys, void* out, i64 n, void* s) override
   {
-    auto const* k = static_cast<key_type const*>(keys);
-    c_.find_async(k, k + n, static_cast<payload_t*>(out), sref(s));
+    if constexpr (is_multimap_v) {
+      throw std::invalid_argument("find is not an experimental::static_multimap operation");
+    } else {
+      auto const* k = static_cast<key_type const*>(keys);
+      c_.find_async(k, k + n, static_cast<payload_t*>(out), sref(s));
+    }
   }
 
   void contains(const void* keys, std::uint8_t* out, i64 n, void* s) override
@@ -199,7 +229,7 @@ class table_impl final : public cuco_b200_table {
 
   void insert_or_assign(const void* keys, const void* values, i64 n, void* s) override
   {
-    if constexpr (is_map) {
+    if constexpr (is_map && !is_multi) {
       with_input(keys, values, n, [&](auto first, auto last) {
         c_.insert_or_assign_async(first, last, sref(s));
       });
@@ -210,7 +240,7 @@ class table_impl final : public cuco_b200_table {
 
   void insert_or_apply(const void* keys, const void* values, i64 n, int op, int has_init, i64 init, void* s) override
   {
-    if constexpr (is_map) {
+    if constexpr (is_map && !is_multi) {
       with_input(keys, values, n, [&](auto first, auto last) {
         auto run = [&](auto functor) {
           if (has_init) {
@@ -267,7 +297,11 @@ class table_impl final : public cuco_b200_table {
 
   i64 count(const void* keys, i64 n, bool outer, void* s) override
   {
-    if constexpr (is_multi) {
+    if constexpr (is_multimap_v) {
+      auto const* k = static_cast<key_type const*>(keys);
+      if (outer) { throw std::invalid_argument("count_outer is a static_multiset operation"); }
+      return static_cast<i64>(c_.count(k, k + n, sref(s)));
+    } else if constexpr (is_multi) {
       auto const* k = static_cast<key_type const*>(keys);
       if (outer) {
         return static_cast<i64>(c_.count_outer(k, k + n, c_.key_eq(), c_.hash_function(), sref(s)));
@@ -283,7 +317,10 @@ class table_impl final : public cuco_b200_table {
     auto const* k = static_cast<key_type const*>(keys);
     auto* p       = static_cast<key_type*>(probe_out);
     auto* m       = static_cast<key_type*>(match_out);
-    if constexpr (is_multi) {
+    if constexpr (is_multimap_v) {
+      (void)k, (void)p, (void)m, (void)n, (void)outer, (void)s;
+      throw std::invalid_argument("retrieve is a static_set / static_multiset operation");
+    } else if constexpr (is_multi) {
       if (outer) {
         return static_cast<i64>(
           c_.retrieve_outer(k, k + n, c_.key_eq(), c_.hash_function(), p, m, sref(s)).first - p);

@@ -77,3 +77,4 @@ CUCO_SHIM_DECLARE_FACTORY(8);
 CUCO_SHIM_DECLARE_FACTORY(9);
 CUCO_SHIM_DECLARE_FACTORY(10);
 CUCO_SHIM_DECLARE_FACTORY(11);
+CUCO_SHIM_DECLARE_FACTORY(12);

@@ -8,6 +8,10 @@
 //  * thread-per-key on the resumable probe cursor of probe_engine, sector-wide read-only loads like
 //    `lookup_kernel`; a key's probe walk ends at the first EMPTY slot, every EQUAL slot on the way is a
 //    match (tables that forbid duplicates stop at the first match);
+//  * walks over tables with duplicates are long (all copies of the key, then the rest of the cluster
+//    up to the first empty slot), so they run with look-ahead (`probe_engine::walk_ahead`): the next
+//    chunks of the probe sequence - under linear probing the other sectors of the 128-byte line DRAM
+//    delivers anyway - are loaded together instead of one dependent round trip per 32-byte chunk;
 //  * retrieve reserves output space once per CTA round: per-thread match counts -> block exclusive
 //    scan -> ONE global atomic per round -> every thread writes its matches at its own offset, so the
 //    output of a round is one contiguous run. The first match of a key is kept in a register during
@@ -38,7 +42,8 @@ __device__ __forceinline__ unsigned int count_matches(Engine const& engine,
   using size_type  = typename Engine::size_type;
   using slot_type  = typename Engine::value_type;
   unsigned int hits = 0;
-  engine.template walk<ChunkSlots, Policy>(engine.make_cursor(key), [&](size_type, slot_type slot) {
+  constexpr int ahead = Engine::template match_walk_ahead<ChunkSlots>();
+  engine.template walk_ahead<ChunkSlots, Policy, ahead>(engine.make_cursor(key), [&](size_type, slot_type slot) {
     auto const state = engine.classify_lookup(key, Engine::key_of(slot));
     if (state == equal_result::EMPTY) { return true; }
     if (state == equal_result::EQUAL) {
@@ -130,7 +135,8 @@ __device__ void block_retrieve(Engine const& engine,
       *(output_match + where) = match;
     } else if (rows > 1) {
       unsigned int written = 0;
-      engine.template walk<ChunkSlots, Policy>(
+      constexpr int ahead = Engine::template match_walk_ahead<ChunkSlots>();
+      engine.template walk_ahead<ChunkSlots, Policy, ahead>(
         engine.make_cursor(key.value), [&](size_type, slot_type slot) {
           auto const state = engine.classify_lookup(key.value, Engine::key_of(slot));
           if (state == equal_result::EMPTY) { return true; }

@@ -3,7 +3,8 @@
  * The reference (NVIDIA/cuCollections) is a header-only C++ template library with no FFI; its
  * boundary for this path is the `cuco::static_map` / `cuco::static_set` class templates
  * (reference include/cuco/static_map.cuh:88-986, include/cuco/static_set.cuh:82-798; next row:
- * `cuco::static_multiset`, include/cuco/static_multiset.cuh:81-729), which this
+ * `cuco::static_multiset`, include/cuco/static_multiset.cuh:81-729, and
+ * `cuco::experimental::static_multimap`, include/cuco/static_multimap.cuh:45-549), which this
  * repository re-implements under include/cuco/. This header is the plain-C view of explicit
  * instantiations of that surface, so that non-C++ hosts (ctypes, cgo, JNI, ...) and the parity /
  * benchmark harness can drive it. Every entry point names the reference member it forwards to.
@@ -46,7 +47,9 @@ enum cuco_b200_kind {
   CUCO_B200_MAP_I64_DH8_X64   = 9, /* static_map<int64,int64>      double_hashing<8, xxhash_64> w1 (tables near 2^32 windows) */
   CUCO_B200_MULTISET_I32_DH4_W2 = 10, /* static_multiset<int32>     double_hashing<4> w2 (class default) */
   CUCO_B200_MULTISET_I64_LP1_W2 = 11, /* static_multiset<int64>     linear_probing<1> w2 */
-  CUCO_B200_NUM_KINDS         = 12
+  CUCO_B200_MULTIMAP_I64_LP4    = 12, /* experimental::static_multimap<int64,int64> linear_probing<4> w1 (class default):
+                                         insert, insert_if, contains, contains_if, count only */
+  CUCO_B200_NUM_KINDS         = 13
 };
 
 /* Reduction selector for cuco_b200_insert_or_apply (cuco::reduce::plus / min / max,
@@ -149,8 +152,10 @@ int cuco_b200_erase(cuco_b200_table* t, const void* keys, int64_t n, void* strea
 int cuco_b200_retrieve_all(
   cuco_b200_table* t, void* keys_out, void* values_out, int64_t* n_out, void* stream);
 
-/* count / count_outer (static_multiset.cuh:615,661): *out (host) = total number of stored elements
- * matching the n keys; outer != 0 counts a key without matches as one. Multisets only. Synchronises. */
+/* count / count_outer (static_multiset.cuh:615,661; experimental::static_multimap::count,
+ * static_multimap.cuh:469): *out (host) = total number of stored elements matching the n keys;
+ * outer != 0 (multisets only) counts a key without matches as one. Multisets and multimaps only.
+ * Synchronises. */
 int cuco_b200_count(
   cuco_b200_table* t, const void* keys, int64_t n, int outer, void* stream, int64_t* out);
 

@@ -124,8 +124,9 @@ KIND_GEOMETRY = {
     9: (8, 8, 8, 1, DOUBLE, XXHASH64),
     10: (4, 0, 4, 2, DOUBLE, XXHASH32),
     11: (8, 0, 1, 2, LINEAR, XXHASH32),
+    12: (8, 8, 4, 1, LINEAR, XXHASH32),
 }
-MULTI_KINDS = {10, 11}  # static_multiset instantiations: equal keys are stored repeatedly
+MULTI_KINDS = {10, 11, 12}  # static_multiset / multimap instantiations: equal keys are stored repeatedly
 
 
 class Table:
@@ -188,6 +189,9 @@ class Table:
             s = np.ascontiguousarray(np.asarray(stencil).astype(np.uint8))
             lib().oracle_contains_if(self._h, _p(k), _p(s), _p(out), k.size)
         return out.astype(bool)
+
+    def contains_if(self, keys, stencil):
+        return self.contains(keys, stencil)
 
     def insert_and_find(self, keys, values=None):
         k = _i64(keys)

@@ -6,10 +6,12 @@
 //   tests/static_set/{unique_sequence,insert_and_find,shared_memory,heterogeneous_lookup,
 //                     retrieve}_test.cu
 //   tests/static_multiset/{insert,contains,find,count,custom_count,retrieve,for_each}_test.cu
+//   tests/static_multimap/{insert_contains,insert_if,count,for_each}_test.cu (experimental::static_multimap)
 //   tests/utility/probing_scheme_test.cu, examples/static_map/device_ref_example.cu,
 //   examples/static_set/device_ref_example.cu, examples/static_map/count_by_key_example.cu
 // Prints one line per check and a JSON summary; exit code 0 iff everything passed.
 #include <cuco/static_map.cuh>
+#include <cuco/static_multimap.cuh>
 #include <cuco/static_multiset.cuh>
 #include <cuco/static_set.cuh>
 #include <cuco/utility/reduction_functors.cuh>
@@ -880,6 +882,110 @@ static void multiset_suite(char const* label)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// experimental::static_multimap (tests/static_multimap/{insert_contains,insert_if,count,for_each}_test.cu)
+// ------------------------------------------------------------------------------------------------
+template <typename Key, typename Value>
+struct make_kv_mod {
+  Key distinct;
+  __host__ __device__ cuco::pair<Key, Value> operator()(std::int64_t i) const
+  {
+    return cuco::pair<Key, Value>{static_cast<Key>(i % distinct), static_cast<Value>(i)};
+  }
+};
+
+template <typename Ref, typename Key>
+__global__ void multimap_ref_kernel(Ref ref, Key n_keys, std::size_t multiplicity, Key distinct, int* errors)
+{
+  constexpr int cgs = Ref::cg_size;
+  auto const tile   = cg::tiled_partition<cgs>(cg::this_thread_block());
+  for (Key k = (blockIdx.x * blockDim.x + threadIdx.x) / cgs; k < n_keys; k += (gridDim.x * blockDim.x) / cgs) {
+    std::size_t mine = 0, bad = 0;
+    auto const on_slot = [&](auto const slot) {
+      ++mine;
+      // payload i was stored under key i % distinct
+      if (slot.first != k || static_cast<Key>(slot.second % distinct) != k) { ++bad; }
+    };
+    std::size_t count = 0;
+    bool present      = false;
+    if constexpr (cgs == 1) {
+      ref.for_each(k, on_slot);
+      count   = ref.count(k);
+      present = ref.contains(k);
+    } else {
+      ref.for_each(tile, k, on_slot);
+      mine    = cg::reduce(tile, mine, cg::plus<std::size_t>());
+      bad     = cg::reduce(tile, bad, cg::plus<std::size_t>());
+      count   = cg::reduce(tile, static_cast<std::size_t>(ref.count(tile, k)), cg::plus<std::size_t>());
+      present = ref.contains(tile, k);
+    }
+    std::size_t const want = k < distinct ? multiplicity : 0;
+    if (tile.thread_rank() == 0) {
+      if (mine != want || bad != 0) { atomicAdd(errors, 1); }
+      if (count != want) { atomicAdd(errors, 1); }
+      if (present != (want != 0)) { atomicAdd(errors, 1); }
+    }
+  }
+}
+
+template <typename Key, typename Value, typename Probe>
+static void multimap_suite(char const* label)
+{
+  std::printf("# experimental::static_multimap, %s\n", label);
+  using extent_type = cuco::extent<std::size_t>;
+  using map_type    = cuco::experimental::static_multimap<Key,
+                                                       Value,
+                                                       extent_type,
+                                                       cuda::thread_scope_device,
+                                                       thrust::equal_to<Key>,
+                                                       Probe,
+                                                       cuco::cuda_allocator<cuda::std::byte>,
+                                                       cuco::storage<2>>;
+  constexpr std::size_t n = 4000, distinct = 500, multiplicity = n / distinct;
+  auto map = map_type{extent_type{2 * n}, cuco::empty_key<Key>{-1}, cuco::empty_value<Value>{-1}};
+  auto const keys  = thrust::counting_iterator<Key>{0};
+  auto const pairs = thrust::make_transform_iterator(
+    thrust::counting_iterator<std::int64_t>{0}, make_kv_mod<Key, Value>{static_cast<Key>(n)});
+  thrust::device_vector<bool> present(n);
+
+  map.contains(keys, keys + n, present.begin());
+  CHECK(none_true(present.begin(), present.end()));
+  CHECK(map.count(keys, keys + n) == 0);
+
+  // unique keys
+  map.insert(pairs, pairs + n);
+  map.contains(keys, keys + n, present.begin());
+  CHECK(all_true(present.begin(), present.end()));
+  CHECK(map.count(keys, keys + n) == n);
+  map.contains_if(keys, keys + n, thrust::counting_iterator<std::size_t>(0), is_even{}, present.begin());
+  CHECK(thrust::count(present.begin(), present.end(), true) == static_cast<std::ptrdiff_t>(n / 2));
+
+  // insert_if: half of the stream, then the same element n / 2 times
+  map.clear();
+  CHECK(map.insert_if(pairs, pairs + n, keys, is_even{}) == n / 2);
+  CHECK(map.count(keys, keys + n) == n / 2);
+  map.clear();
+  auto const same = thrust::constant_iterator<cuco::pair<Key, Value>>{{1, 1}};
+  CHECK(map.insert_if(same, same + n, keys, is_even{}) == n / 2);
+  CHECK(map.count(keys, keys + n) == n / 2);
+
+  // every key `multiplicity` times; device ref: for_each / count / contains
+  map.clear();
+  auto const dup_pairs = thrust::make_transform_iterator(
+    thrust::counting_iterator<std::int64_t>{0}, make_kv_mod<Key, Value>{static_cast<Key>(distinct)});
+  map.insert_async(dup_pairs, dup_pairs + n);
+  CHECK(map.count(keys, keys + n) == n);
+  CHECK(map.count(keys, keys + distinct / 2) == n / 2);
+  thrust::device_vector<int> errors(1, 0);
+  multimap_ref_kernel<<<8, 128>>>(map.ref(cuco::for_each, cuco::count, cuco::contains),
+                                  static_cast<Key>(2 * distinct),
+                                  multiplicity,
+                                  static_cast<Key>(distinct),
+                                  errors.data().get());
+  cudaDeviceSynchronize();
+  CHECK(errors[0] == 0);
+}
+
 int main()
 {
   bulk_api_suite<std::int64_t, std::int64_t, cuco::linear_probing<1, cuco::default_hash_function<std::int64_t>>, 1>(
@@ -917,6 +1023,14 @@ int main()
     "int64 double_hashing<2> storage<2>");
   multiset_suite<std::int32_t, cuco::linear_probing<1, cuco::default_hash_function<std::int32_t>>>(
     "int32 linear_probing<1> storage<2>");
+  multimap_suite<std::int32_t, std::int32_t, cuco::double_hashing<2, cuco::murmurhash3_32<std::int32_t>, cuco::murmurhash3_32<std::int32_t>>>(
+    "int32/int32 double_hashing<2, murmur> storage<2>");
+  multimap_suite<std::int64_t, std::int64_t, cuco::linear_probing<1, cuco::murmurhash3_32<std::int64_t>>>(
+    "int64/int64 linear_probing<1, murmur> storage<2>");
+  multimap_suite<std::int32_t, std::int64_t, cuco::linear_probing<2, cuco::murmurhash3_32<std::int32_t>>>(
+    "int32/int64 linear_probing<2, murmur> storage<2> (padded slots)");
+  multimap_suite<std::int64_t, std::int32_t, cuco::double_hashing<1, cuco::murmurhash3_32<std::int64_t>, cuco::murmurhash3_32<std::int64_t>>>(
+    "int64/int32 double_hashing<1, murmur> storage<2> (padded slots)");
   cudaDeviceSynchronize();
   bool const cuda_ok = cudaGetLastError() == cudaSuccess;
   report(cuda_ok, "no CUDA error at exit");

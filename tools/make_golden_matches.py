@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """Generates tests/golden/cuco_golden_matches.npz: outputs of cuCollections' OWN implementation
-(oracle/_ref/libcuco_ref.so) for the rows next to the hot path - `static_set::retrieve` and
+(oracle/_ref/libcuco_ref.so) for the rows next to the hot path - `static_set::retrieve`,
 `static_multiset` insert / insert_if / contains / find / count / count_outer / retrieve /
-retrieve_outer - on seeded inputs, run on a B200.
+retrieve_outer and `experimental::static_multimap` insert / insert_if / contains / contains_if /
+count - on seeded inputs, run on a B200.
 
 Run on the GPU box:  python tools/make_golden_matches.py gpurun_out/golden/cuco_golden_matches.npz
 then copy the file to tests/golden/. `run_kind` is the recorded scenario; tests/
@@ -18,8 +19,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 N = 3000
 SEED = 20241017
-KINDS = (0, 5, 10, 11)  # static_set<int32>, static_set<int64>, static_multiset<int32>, <int64>
-MULTI = (10, 11)
+KINDS = (0, 5, 10, 11, 12)  # static_set<int32>, <int64>, static_multiset<int32>, <int64>, multimap<int64,int64>
+MULTISETS = (10, 11)
+MULTIMAPS = (12,)
 
 
 def inputs(kind: int):
@@ -55,10 +57,15 @@ class GpuBackend:
         k = self.k
         common = dict(key_dtype=k.key, probing=k.probing, cg_size=k.cg_size, window_size=k.window_size,
                       hash=k.hash, device=self.torch.device("cuda", 0), _library=self.lib, **kw)
+        if k.value is not None:
+            return self.cb.static_multimap(value_dtype=k.value, **common)
         return self.cb.static_multiset(**common) if k.multi else self.cb.static_set(**common)
 
     def keys(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to("cuda").to(self.k.key)
+
+    def values(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to("cuda").to(self.k.value)
 
     def stencil(self, s):
         return self.torch.from_numpy(s).to("cuda")
@@ -84,6 +91,10 @@ class OracleBackend:
         return a
 
     @staticmethod
+    def values(a):
+        return a
+
+    @staticmethod
     def stencil(s):
         return s
 
@@ -96,7 +107,6 @@ def run_scenario(kind, b):
     a, q, stencil = inputs(kind)
     tag = f"k{kind}_"
     out = {tag + "a": a, tag + "q": q, tag + "stencil": stencil}
-    multi = kind in MULTI
 
     caps = []
     for lf in (0.5, 0.8, 1.0):
@@ -106,13 +116,23 @@ def run_scenario(kind, b):
     out[tag + "capacities"] = np.asarray(caps, dtype=np.int64)
 
     t = b.make(n=2 * N, load_factor=0.7)  # insert_if (~N/2) + insert (N) elements stay below capacity
+    if kind in MULTIMAPS:
+        vals = a * 3 + 1
+        out[tag + "insert_if_new"] = np.int64(t.insert_if(b.keys(a), b.stencil(stencil), b.values(vals)))
+        out[tag + "count_after_insert_if"] = np.int64(t.count(b.keys(q)))
+        out[tag + "insert_new"] = np.int64(t.insert(b.keys(a), b.values(vals)))
+        out[tag + "contains_q"] = b.host(t.contains(b.keys(q))).astype(bool)
+        out[tag + "contains_if_q"] = b.host(t.contains_if(b.keys(q), b.stencil(stencil[: q.size]))).astype(bool)
+        out[tag + "count_inner"] = np.int64(t.count(b.keys(q)))
+        out[tag + "count_self"] = np.int64(t.count(b.keys(a)))
+        return out
     out[tag + "insert_if_new"] = np.int64(t.insert_if(b.keys(a), b.stencil(stencil)))
     out[tag + "size_after_insert_if"] = np.int64(t.size())
     out[tag + "insert_new"] = np.int64(t.insert(b.keys(a)))
     out[tag + "size"] = np.int64(t.size())
     out[tag + "contains_q"] = b.host(t.contains(b.keys(q))).astype(bool)
     out[tag + "find_q"] = b.host(t.find(b.keys(q))).astype(np.int64)
-    if multi:
+    if kind in MULTISETS:
         for outer in (False, True):
             name = "outer" if outer else "inner"
             out[tag + f"count_{name}"] = np.int64(t.count(b.keys(q), outer))
