@@ -73,6 +73,8 @@ struct tuning_t {
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
   int exchange_lookup_keys_per_thread = 2;  ///< owner side of routed lookups (1, 2 or 4)
   std::size_t l2_window_bytes = std::size_t{48} << 20;
+  int match_ahead = 1;  ///< count / retrieve on tables with duplicates: chunks of the probe sequence
+                        ///< loaded together while they stay inside one 128-byte line (1, 2 or 4)
 };
 
 inline tuning_t tuning_from_env()
@@ -93,6 +95,7 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_EXCHANGE_LOOKUP_KPT")) {
     t.exchange_lookup_keys_per_thread = std::atoi(s);
   }
+  if (char const* s = std::getenv("CUCO_B200_MATCH_AHEAD")) { t.match_ahead = std::atoi(s); }
   if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
     t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
   }
@@ -475,10 +478,12 @@ class table_engine {
     auto* counter     = this->zeroed_counter(stream);
     auto const grid   = generic_grid(n);
     if (this->fast_path_ok(false)) {
-      count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots>
-        <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+      with_match_ahead<engine_t>([&](auto ahead) {
+        count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
+          <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+      });
     } else {
-      count_kernel<IsOuter, block_size, engine_t::window_chunk_slots>
+      count_kernel<IsOuter, block_size, engine_t::window_chunk_slots, 1>
         <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
     }
     return this->read_counter(stream);
@@ -508,10 +513,12 @@ class table_engine {
     auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
       cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
     if (this->fast_path_ok(false)) {
-      retrieve_kernel<IsOuter, block_size, engine_t::sector_chunk_slots>
-        <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
+      with_match_ahead<engine_t>([&](auto ahead) {
+        retrieve_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
+          <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
+      });
     } else {
-      retrieve_kernel<IsOuter, block_size, engine_t::window_chunk_slots>
+      retrieve_kernel<IsOuter, block_size, engine_t::window_chunk_slots, 1>
         <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
     }
     return this->read_counter(stream);
@@ -617,6 +624,21 @@ class table_engine {
     auto const blocks = cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size});
     auto const cap    = static_cast<cuco::detail::index_type>(cuco::detail::multiprocessor_count()) * 16;
     return static_cast<unsigned>(std::max<cuco::detail::index_type>(1, std::min(blocks, cap)));
+  }
+
+  /// Look-ahead depth of the all-matches walks: only tables with duplicates have long walks.
+  template <typename EngineT, typename Run>
+  static void with_match_ahead(Run&& run)
+  {
+    if constexpr (!EngineT::allows_duplicates) {
+      run(std::integral_constant<int, 1>{});
+    } else {
+      switch (tuning().match_ahead) {
+        case 4: run(std::integral_constant<int, 4>{}); break;
+        case 2: run(std::integral_constant<int, 2>{}); break;
+        default: run(std::integral_constant<int, 1>{}); break;
+      }
+    }
   }
 
   /// Can the sector-chunk, single-CAS kernels run on this table right now?

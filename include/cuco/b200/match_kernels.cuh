@@ -9,9 +9,10 @@
 //    `lookup_kernel`; a key's probe walk ends at the first EMPTY slot, every EQUAL slot on the way is a
 //    match (tables that forbid duplicates stop at the first match);
 //  * walks over tables with duplicates are long (all copies of the key, then the rest of the cluster
-//    up to the first empty slot), so they run with look-ahead (`probe_engine::walk_ahead`): the next
-//    chunks of the probe sequence - under linear probing the other sectors of the 128-byte line DRAM
-//    delivers anyway - are loaded together instead of one dependent round trip per 32-byte chunk;
+//    up to the first empty slot), so they can run with look-ahead (`probe_engine::walk_ahead`,
+//    tuning().match_ahead): the following chunks of the probe sequence that lie in the same 128-byte
+//    line - which DRAM delivers whole anyway - are loaded together instead of one dependent round
+//    trip per 32-byte chunk;
 //  * retrieve reserves output space once per CTA round: per-thread match counts -> block exclusive
 //    scan -> ONE global atomic per round -> every thread writes its matches at its own offset, so the
 //    output of a round is one contiguous run. The first match of a key is kept in a register during
@@ -34,7 +35,7 @@
 namespace cuco::b200 {
 
 /// Number of slots matching `key` (walk ends at the first empty slot), remembering the first match.
-template <int ChunkSlots, load_policy Policy, typename Engine, typename ProbeKey>
+template <int ChunkSlots, load_policy Policy, int Ahead, typename Engine, typename ProbeKey>
 __device__ __forceinline__ unsigned int count_matches(Engine const& engine,
                                                       ProbeKey const& key,
                                                       typename Engine::value_type& first_match)
@@ -42,8 +43,7 @@ __device__ __forceinline__ unsigned int count_matches(Engine const& engine,
   using size_type  = typename Engine::size_type;
   using slot_type  = typename Engine::value_type;
   unsigned int hits = 0;
-  constexpr int ahead = Engine::template match_walk_ahead<ChunkSlots>();
-  engine.template walk_ahead<ChunkSlots, Policy, ahead>(engine.make_cursor(key), [&](size_type, slot_type slot) {
+  engine.template walk_ahead<ChunkSlots, Policy, Ahead>(engine.make_cursor(key), [&](size_type, slot_type slot) {
     auto const state = engine.classify_lookup(key, Engine::key_of(slot));
     if (state == equal_result::EMPTY) { return true; }
     if (state == equal_result::EQUAL) {
@@ -93,6 +93,7 @@ template <bool IsOuter,
           int BlockSize,
           int ChunkSlots,
           load_policy Policy,
+          int Ahead,
           typename Engine,
           typename InputIt,
           typename OutputProbeIt,
@@ -118,7 +119,7 @@ __device__ void block_retrieve(Engine const& engine,
     unsigned int hits = 0, rows = 0;
     if (idx < n) {
       key.value = read_input(first, idx);
-      hits      = count_matches<ChunkSlots, Policy>(engine, key.value, match);
+      hits      = count_matches<ChunkSlots, Policy, Ahead>(engine, key.value, match);
       rows      = (IsOuter && hits == 0) ? 1u : hits;
     }
     unsigned int offset, total;
@@ -135,8 +136,7 @@ __device__ void block_retrieve(Engine const& engine,
       *(output_match + where) = match;
     } else if (rows > 1) {
       unsigned int written = 0;
-      constexpr int ahead = Engine::template match_walk_ahead<ChunkSlots>();
-      engine.template walk_ahead<ChunkSlots, Policy, ahead>(
+      engine.template walk_ahead<ChunkSlots, Policy, Ahead>(
         engine.make_cursor(key.value), [&](size_type, slot_type slot) {
           auto const state = engine.classify_lookup(key.value, Engine::key_of(slot));
           if (state == equal_result::EMPTY) { return true; }
@@ -167,6 +167,7 @@ struct global_counter {
 template <bool IsOuter,
           int BlockSize,
           int ChunkSlots,
+          int Ahead,
           typename InputIt,
           typename OutputProbeIt,
           typename OutputMatchIt,
@@ -187,11 +188,17 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void retrieve_kernel(InputIt first,
   if (begin >= n) { return; }
   index_type const count = (n - begin) < span ? (n - begin) : span;
   global_counter<Counter> counter{num_rows};
-  block_retrieve<IsOuter, BlockSize, ChunkSlots, load_policy::readonly>(
+  block_retrieve<IsOuter, BlockSize, ChunkSlots, load_policy::readonly, Ahead>(
     engine, first + begin, count, output_probe, output_match, counter);
 }
 
-template <bool IsOuter, int BlockSize, int ChunkSlots, typename InputIt, typename Counter, typename Engine>
+template <bool IsOuter,
+          int BlockSize,
+          int ChunkSlots,
+          int Ahead,
+          typename InputIt,
+          typename Counter,
+          typename Engine>
 CUCO_KERNEL __launch_bounds__(BlockSize) void count_kernel(InputIt first,
                                                            index_type n,
                                                            Counter* total,
@@ -203,7 +210,8 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void count_kernel(InputIt first,
        idx += cuco::detail::grid_stride()) {
     auto const key = read_input(first, idx);
     slot_type unused = engine.empty_slot_sentinel();
-    unsigned int const hits = count_matches<ChunkSlots, load_policy::readonly>(engine, key, unused);
+    unsigned int const hits =
+      count_matches<ChunkSlots, load_policy::readonly, Ahead>(engine, key, unused);
     mine += (IsOuter && hits == 0) ? 1u : hits;
   }
   accumulate_count(total, mine);

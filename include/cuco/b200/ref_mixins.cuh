@@ -223,7 +223,7 @@ struct mixin_retrieve : mixin_base<Ref, op::retrieve_tag> {
   {
     auto const& e  = this->self().engine();
     using engine_t = cuda::std::remove_cv_t<cuda::std::remove_reference_t<decltype(e)>>;
-    block_retrieve<IsOuter, BlockSize, engine_t::window_chunk_slots, load_policy::plain>(
+    block_retrieve<IsOuter, BlockSize, engine_t::window_chunk_slots, load_policy::plain, 1>(
       e, first, static_cast<cuco::detail::index_type>(last - first), out_probe, out_match, counter);
   }
 };

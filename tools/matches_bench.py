@@ -6,6 +6,7 @@ cuco's own build through the same shim, outputs cross-checked:
   retrieve with n/2 probes (50 % hits).
 The synchronous calls (count, retrieve) are timed by wall clock around the call; insert by events."""
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -46,10 +47,11 @@ def best(fn, reps=3):
 
 
 libs = [("native", _cabi.native())]
-try:
-    libs.append(("reference", _cabi.reference()))
-except (FileNotFoundError, OSError):
-    pass
+if not os.environ.get("MATCHES_NATIVE_ONLY"):
+    try:
+        libs.append(("reference", _cabi.reference()))
+    except (FileNotFoundError, OSError):
+        pass
 
 set_keys = torch.randperm(n, device=dev, dtype=torch.int64)
 set_probes = torch.randperm(2 * n, device=dev, dtype=torch.int64)
@@ -77,7 +79,7 @@ for name, lib in libs:
     multi_ok = bool(torch.equal(p, m))
     hist = torch.bincount(p, minlength=n // 2)
     rows.append({
-        "impl": name, "n": n,
+        "impl": name, "n": n, "match_ahead": int(os.environ.get("CUCO_B200_MATCH_AHEAD", "1")),
         "set_insert_gops": round(n / set_insert_ms / 1e6, 2),
         "set_retrieve_gprobes": round(2 * n / set_retrieve_ms / 1e6, 2), "set_retrieve_rows": set_rows,
         "multiset_insert_gops": round(n / multi_insert_ms / 1e6, 2),
