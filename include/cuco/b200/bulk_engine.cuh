@@ -73,9 +73,11 @@ struct tuning_t {
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
   int exchange_lookup_keys_per_thread = 2;  ///< owner side of routed lookups (1, 2 or 4)
   std::size_t l2_window_bytes = std::size_t{48} << 20;
-  int match_ahead = 1;  ///< retrieve on tables with duplicates: chunks of the probe sequence loaded
-                        ///< together while they stay inside one 128-byte line (1, 2 or 4). Measured on
-                        ///< B200 (profiles/r01_matches_ahead.jsonl): 2 and 4 lose 10 % / 48 %, so 1
+  int match_ahead = 1;  ///< count / retrieve on tables with duplicates: chunks of the probe sequence
+                        ///< loaded together while they stay inside one 128-byte line (1, 2 or 4).
+                        ///< Measured on B200 (profiles/r01_matches_ahead.jsonl, multiplicity 4):
+                        ///< count 13.6 / 15.0 / 13.6 G probes/s, retrieve 11.6 / 10.5 / 6.1 G rows/s
+                        ///< for 1 / 2 / 4, so 1 stays the default
 };
 
 inline tuning_t tuning_from_env()
@@ -479,10 +481,12 @@ class table_engine {
     auto* counter     = this->zeroed_counter(stream);
     auto const grid   = generic_grid(n);
     if (this->fast_path_ok(false)) {
-      count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots>
-        <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+      with_match_ahead<engine_t>([&](auto ahead) {
+        count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
+          <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
+      });
     } else {
-      count_kernel<IsOuter, block_size, engine_t::window_chunk_slots>
+      count_kernel<IsOuter, block_size, engine_t::window_chunk_slots, 1>
         <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
     }
     return this->read_counter(stream);
@@ -511,18 +515,6 @@ class table_engine {
     // one CTA per round of 256 keys (like the other random-probe kernels)
     auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
       cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
-    if constexpr (!engine_t::allows_duplicates) {
-      if (this->fast_path_ok(false)) {
-        constexpr int kpt = 2;
-        auto const tiles  = cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size} * kpt);
-        retrieve_unique_kernel<IsOuter, block_size, kpt, engine_t::sector_chunk_slots>
-          <<<static_cast<unsigned>(std::min<cuco::detail::index_type>(tiles, 0x7fffffff)),
-             block_size,
-             0,
-             stream.get()>>>(in, n, out_probe, out_match, counter, engine);
-        return this->read_counter(stream);
-      }
-    }
     if (this->fast_path_ok(false)) {
       with_match_ahead<engine_t>([&](auto ahead) {
         retrieve_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>

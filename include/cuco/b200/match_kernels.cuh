@@ -18,11 +18,15 @@
 //    output of a round is one contiguous run. The first match of a key is kept in a register during
 //    the counting walk; only keys with more than one match walk their (now L1/L2-resident) probe
 //    sequence a second time. No shared-memory flush buffers, no per-match atomics;
-//  * tables without duplicates (static_set::retrieve) take `retrieve_unique_kernel`: the lookup
-//    kernel's multi-key probe phase with the match kept in registers, then the same reservation;
-//  * `count` runs a flattened loop (a lane that finishes a key picks up its next one at once), because
-//    walk lengths differ widely inside a warp;
 //  * `outer` variants account a key without matches as one output row {key, empty slot sentinel}.
+//
+// Tried and measured on B200, not kept (profiles/r01_matches_bench_v2_flattened.jsonl,
+// profiles/r01_ncu_count_kernel_v1_details.txt): the per-key count loop runs with 7.7 of 32 lanes
+// active (walk lengths differ widely inside a warp), but a flattened loop in which a lane that
+// finishes a key fetches its next one at once was SLOWER (11.6 vs 13.6 G probes/s: the key loads
+// stop being coalesced and nearly every iteration pays the refill path for a few lanes); a
+// lookup-kernel-style probe phase (two keys per thread in flight) for tables without duplicates
+// changed nothing (32.1 vs 31.7 G probes/s), so the one `block_retrieve` serves both.
 //
 // The order of the output rows is unspecified by contract (reference: "copies ... to unspecified
 // locations"); parity is defined on the multiset of rows.
@@ -196,126 +200,10 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void retrieve_kernel(InputIt first,
     engine, first + begin, count, output_probe, output_match, counter);
 }
 
-/// retrieve on tables WITHOUT duplicates (static_set::retrieve, the join probe): at most one match
-/// per key, so the probe phase is the lookup kernel's - KeysPerThread independent cursors per thread,
-/// every pending chunk load posted before any is consumed - with the match kept in a register
-/// instead of being written at the key's input position; then ONE block scan and ONE global atomic
-/// per tile reserve the output run and every thread writes its rows behind its own prefix.
-template <bool IsOuter,
-          int BlockSize,
-          int KeysPerThread,
-          int ChunkSlots,
-          typename InputIt,
-          typename OutputProbeIt,
-          typename OutputMatchIt,
-          typename Counter,
-          typename Engine>
-CUCO_KERNEL __launch_bounds__(BlockSize) void retrieve_unique_kernel(InputIt first,
-                                                                     index_type n,
-                                                                     OutputProbeIt output_probe,
-                                                                     OutputMatchIt output_match,
-                                                                     Counter* num_rows,
-                                                                     Engine engine)
-{
-  static_assert(!Engine::allows_duplicates);
-  using slot_type  = typename Engine::value_type;
-  using cursor     = typename Engine::cursor;
-  using probe_type = decltype(read_input(first, index_type{0}));
-  constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
-  constexpr auto policy     = load_policy::readonly;
-  __shared__ unsigned int warp_totals[BlockSize / 32];
-  __shared__ unsigned long long tile_base_row;
-
-  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
-       tile_base += index_type{gridDim.x} * tile) {
-    uninitialized<probe_type> key[KeysPerThread];
-    slot_type match[KeysPerThread];
-    cursor cur[KeysPerThread];
-    unsigned pending = 0, live = 0, hit = 0;
-
-#pragma unroll
-    for (int j = 0; j < KeysPerThread; ++j) {
-      // thread t owns KeysPerThread CONSECUTIVE keys so that its output rows keep the input order
-      index_type const idx = tile_base + index_type{threadIdx.x} * KeysPerThread + j;
-      if (idx < n) {
-        key[j].value = read_input(first, idx);
-        pending |= 1u << j;
-      }
-      match[j] = engine.empty_slot_sentinel();
-    }
-    live = pending;
-#pragma unroll
-    for (int j = 0; j < KeysPerThread; ++j) {
-      if (pending & (1u << j)) { cur[j] = engine.make_cursor(key[j].value); }
-    }
-
-    while (pending) {
-      raw_chunk<ChunkSlots * Engine::slot_bytes> raw[KeysPerThread];
-#pragma unroll
-      for (int j = 0; j < KeysPerThread; ++j) {
-        if (pending & (1u << j)) { raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]); }
-      }
-#pragma unroll
-      for (int j = 0; j < KeysPerThread; ++j) {
-        if (pending & (1u << j)) {
-          int const begin_off =
-            static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
-          int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
-          bool done       = false;
-#pragma unroll
-          for (int i = 0; i < ChunkSlots; ++i) {
-            if (!done && i >= begin_off && i < begin_off + valid) {
-              auto const slot  = chunk_slot<slot_type>(raw[j], i);
-              auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
-              if (state == equal_result::EQUAL) {
-                match[j] = slot;
-                hit |= 1u << j;
-                done = true;
-              } else if (state == equal_result::EMPTY) {
-                done = true;
-              }
-            }
-          }
-          if (done) {
-            pending &= ~(1u << j);
-          } else {
-            engine.advance(cur[j], valid);
-          }
-        }
-      }
-    }
-
-    unsigned const emit = IsOuter ? live : hit;
-    unsigned int offset, total;
-    block_exclusive_scan<BlockSize>(__popc(emit), warp_totals, offset, total);
-    if (total == 0) { continue; }  // uniform across the CTA
-    if (threadIdx.x == 0) {
-      cuda::atomic_ref<Counter, cuda::thread_scope_device> ref{*num_rows};
-      tile_base_row = static_cast<unsigned long long>(
-        ref.fetch_add(static_cast<Counter>(total), cuda::memory_order_relaxed));
-    }
-    __syncthreads();
-    index_type where = static_cast<index_type>(tile_base_row) + offset;
-#pragma unroll
-    for (int j = 0; j < KeysPerThread; ++j) {
-      if (emit & (1u << j)) {
-        *(output_probe + where) = key[j].value;
-        *(output_match + where) = match[j];
-        ++where;
-      }
-    }
-    __syncthreads();  // tile_base_row is rewritten by the next tile
-  }
-}
-
-/// count / count_outer. The walk lengths differ widely between the lanes of a warp (a miss ends at
-/// the first empty slot, a hit walks past all copies of its key and the rest of the cluster), so the
-/// loop is flattened: one iteration is one chunk step of whatever key the lane currently holds, and
-/// a lane that finishes a key fetches its next one in the same iteration structure instead of idling
-/// until the slowest lane of the warp is done (ncu on the per-key loop: 7.7 of 32 lanes active).
 template <bool IsOuter,
           int BlockSize,
           int ChunkSlots,
+          int Ahead,
           typename InputIt,
           typename Counter,
           typename Engine>
@@ -324,52 +212,15 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void count_kernel(InputIt first,
                                                            Counter* total,
                                                            Engine engine)
 {
-  using slot_type  = typename Engine::value_type;
-  using cursor     = typename Engine::cursor;
-  using probe_type = decltype(read_input(first, index_type{0}));
-  constexpr auto policy = load_policy::readonly;
-
+  using slot_type = typename Engine::value_type;
   unsigned long long mine = 0;
-  index_type idx          = cuco::detail::global_thread_id();
-  index_type const stride = cuco::detail::grid_stride();
-  uninitialized<probe_type> key;
-  cursor cur{};
-  unsigned int hits = 0;
-  bool holding      = false;
-
-  while (true) {
-    if (!holding) {
-      if (idx >= n) { break; }
-      key.value = read_input(first, idx);
-      cur       = engine.make_cursor(key.value);
-      hits      = 0;
-      holding   = true;
-      idx += stride;
-    }
-    auto const raw = engine.template load_chunk<ChunkSlots, policy>(cur);
-    int const begin_off =
-      static_cast<int>(cur.slot - Engine::template chunk_begin<ChunkSlots>(cur));
-    int const valid = engine.template chunk_valid<ChunkSlots>(cur);
-    bool done       = false;
-#pragma unroll
-    for (int i = 0; i < ChunkSlots; ++i) {
-      if (!done && i >= begin_off && i < begin_off + valid) {
-        auto const state =
-          engine.classify_lookup(key.value, Engine::key_of(chunk_slot<slot_type>(raw, i)));
-        if (state == equal_result::EMPTY) {
-          done = true;
-        } else if (state == equal_result::EQUAL) {
-          ++hits;
-          if constexpr (!Engine::allows_duplicates) { done = true; }
-        }
-      }
-    }
-    if (done) {
-      mine += (IsOuter && hits == 0) ? 1u : hits;
-      holding = false;
-    } else {
-      engine.advance(cur, valid);
-    }
+  for (index_type idx = cuco::detail::global_thread_id(); idx < n;
+       idx += cuco::detail::grid_stride()) {
+    auto const key = read_input(first, idx);
+    slot_type unused = engine.empty_slot_sentinel();
+    unsigned int const hits =
+      count_matches<ChunkSlots, load_policy::readonly, Ahead>(engine, key, unused);
+    mine += (IsOuter && hits == 0) ? 1u : hits;
   }
   accumulate_count(total, mine);
 }
