@@ -9,3 +9,5 @@ timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke
 echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 140 python bench.py > gpurun_out/bench_native_r01b.json 2> gpurun_out/bench_native_r01b.err
 echo "bench rc=$?"; cut -c1-700 gpurun_out/bench_native_r01b.json; tail -2 gpurun_out/bench_native_r01b.err
+timeout 120 python tools/matches_bench.py 50000000 > gpurun_out/matches_bench.jsonl 2> gpurun_out/matches_bench.err
+echo "matches_bench rc=$?"; cat gpurun_out/matches_bench.jsonl
