@@ -15,9 +15,9 @@
 //    trip per 32-byte chunk;
 //  * retrieve reserves output space once per CTA round: per-thread match counts -> block exclusive
 //    scan -> ONE global atomic per round -> every thread writes its matches at its own offset, so the
-//    output of a round is one contiguous run. The first match of a key is kept in a register during
-//    the counting walk; only keys with more than one match walk their (now L1/L2-resident) probe
-//    sequence a second time. No shared-memory flush buffers, no per-match atomics;
+//    output of a round is one contiguous run. The first matches of a key (up to 32 bytes worth) stay
+//    in registers during the counting walk; only keys with more matches walk their (now L1/L2-
+//    resident) probe sequence a second time. No shared-memory flush buffers, no per-match atomics;
 //  * `outer` variants account a key without matches as one output row {key, empty slot sentinel}.
 //
 // Tried and measured on B200, not kept (profiles/r01_matches_bench_v2_flattened.jsonl,
@@ -42,11 +42,12 @@
 
 namespace cuco::b200 {
 
-/// Number of slots matching `key` (walk ends at the first empty slot), remembering the first match.
-template <int ChunkSlots, load_policy Policy, int Ahead, typename Engine, typename ProbeKey>
+/// Number of slots matching `key` (walk ends at the first empty slot); the first `Cached` matches
+/// are kept in `cache` (registers: the index is resolved by an unrolled compare, never dynamically).
+template <int ChunkSlots, load_policy Policy, int Ahead, int Cached, typename Engine, typename ProbeKey>
 __device__ __forceinline__ unsigned int count_matches(Engine const& engine,
                                                       ProbeKey const& key,
-                                                      typename Engine::value_type& first_match)
+                                                      typename Engine::value_type (&cache)[Cached])
 {
   using size_type  = typename Engine::size_type;
   using slot_type  = typename Engine::value_type;
@@ -55,13 +56,28 @@ __device__ __forceinline__ unsigned int count_matches(Engine const& engine,
     auto const state = engine.classify_lookup(key, Engine::key_of(slot));
     if (state == equal_result::EMPTY) { return true; }
     if (state == equal_result::EQUAL) {
-      if (hits == 0) { first_match = slot; }
+#pragma unroll
+      for (int k = 0; k < Cached; ++k) {
+        if (hits == static_cast<unsigned>(k)) { cache[k] = slot; }
+      }
       ++hits;
       if constexpr (!Engine::allows_duplicates) { return true; }
     }
     return false;
   });
   return hits;
+}
+
+/// Matches of one key kept in registers by `block_retrieve`: one for tables without duplicates,
+/// otherwise as many as fit 32 bytes. Keys with more matches walk their probe sequence again.
+template <typename Engine>
+constexpr int cached_matches() noexcept
+{
+  if constexpr (!Engine::allows_duplicates) {
+    return 1;
+  } else {
+    return Engine::slot_bytes <= 8 ? 4 : 2;
+  }
 }
 
 /// Exclusive scan of one value per thread over the CTA; returns {exclusive prefix, CTA total}.
@@ -123,7 +139,9 @@ __device__ void block_retrieve(Engine const& engine,
   for (index_type base = 0; base < n; base += BlockSize) {
     index_type const idx = base + threadIdx.x;
     uninitialized<probe_type> key;
-    slot_type match = engine.empty_slot_sentinel();
+    constexpr int cached = cached_matches<Engine>();
+    slot_type match[cached];
+    match[0]          = engine.empty_slot_sentinel();  // the row of an outer retrieve without matches
     unsigned int hits = 0, rows = 0;
     if (idx < n) {
       key.value = read_input(first, idx);
@@ -139,10 +157,15 @@ __device__ void block_retrieve(Engine const& engine,
     }
     __syncthreads();
     auto const where = static_cast<index_type>(round_base) + offset;
-    if (rows == 1) {
-      *(output_probe + where) = key.value;
-      *(output_match + where) = match;
-    } else if (rows > 1) {
+    if (rows != 0 && rows <= static_cast<unsigned>(cached)) {
+#pragma unroll
+      for (int k = 0; k < cached; ++k) {
+        if (static_cast<unsigned>(k) < rows) {
+          *(output_probe + (where + k)) = key.value;
+          *(output_match + (where + k)) = match[k];
+        }
+      }
+    } else if (rows != 0) {
       unsigned int written = 0;
       engine.template walk_ahead<ChunkSlots, Policy, Ahead>(
         engine.make_cursor(key.value), [&](size_type, slot_type slot) {
@@ -217,7 +240,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void count_kernel(InputIt first,
   for (index_type idx = cuco::detail::global_thread_id(); idx < n;
        idx += cuco::detail::grid_stride()) {
     auto const key = read_input(first, idx);
-    slot_type unused = engine.empty_slot_sentinel();
+    slot_type unused[1];
     unsigned int const hits =
       count_matches<ChunkSlots, load_policy::readonly, Ahead>(engine, key, unused);
     mine += (IsOuter && hits == 0) ? 1u : hits;

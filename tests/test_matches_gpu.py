@@ -226,6 +226,35 @@ def test_native_matches_golden_fixtures(kind, native_lib):
         assert np.array_equal(got[name], g[name]), name
 
 
+def test_empty_inputs_and_high_multiplicity(native_lib):
+    """n == 0 returns without launching (impl.cuh:335 convention); a key stored more often than the
+    retrieve kernel keeps matches in registers takes the second-walk path."""
+    kind = _cabi.MULTISET_I64_LP1_W2
+    k = cb.KINDS[kind]
+    t = make(kind, native_lib, capacity=4096)
+    empty = torch.empty(0, dtype=k.key, device="cuda")
+    assert t.count(empty) == 0 and t.count(empty, outer=True) == 0
+    p, m = t.retrieve(empty)
+    assert p.numel() == 0 and m.numel() == 0
+    assert t.insert(empty) == 0 and t.size() == 0
+    mult = np.array([1, 2, 3, 4, 5, 9, 33, 100], dtype=np.int64)          # key i stored mult[i] times
+    keys = np.repeat(np.arange(mult.size, dtype=np.int64), mult)
+    np.random.default_rng(3).shuffle(keys)
+    t.insert(dev(keys, k.key))
+    probes = np.arange(0, mult.size + 3, dtype=np.int64)
+    assert t.count(dev(probes, k.key)) == int(mult.sum())
+    p, m = t.retrieve(dev(probes, k.key))
+    assert torch.equal(p, m)
+    assert np.array_equal(np.bincount(p.cpu().numpy(), minlength=probes.size)[: mult.size], mult)
+    p, m = t.retrieve(dev(probes, k.key), outer=True)
+    assert p.numel() == int(mult.sum()) + 3 and int((m == -1).sum().item()) == 3
+    t.close()
+    s = make(_cabi.SET_I64_DH4, native_lib, capacity=1000)
+    p, m = s.retrieve(empty)
+    assert p.numel() == 0
+    s.close()
+
+
 def test_multiset_large_input_properties(native_lib):
     """Size-independent properties at a size the oracle does not reach (large_input_test.cu style):
     40 M elements, each key stored 4 times."""
