@@ -11,7 +11,6 @@
 #pragma once
 
 #include <cuco/b200/bulk_engine.cuh>
-#include <cuco/b200/table_scan.cuh>
 #include <cuco/detail/__config>
 #include <cuco/extent.cuh>
 #include <cuco/hash_functions.cuh>
