@@ -73,11 +73,11 @@ struct tuning_t {
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
   int exchange_lookup_keys_per_thread = 2;  ///< owner side of routed lookups (1, 2 or 4)
   std::size_t l2_window_bytes = std::size_t{48} << 20;
-  int match_ahead = 1;  ///< count / retrieve on tables with duplicates: chunks of the probe sequence
-                        ///< loaded together while they stay inside one 128-byte line (1, 2 or 4).
-                        ///< Measured on B200 (profiles/r01_matches_ahead.jsonl, multiplicity 4):
-                        ///< count 13.6 / 15.0 / 13.6 G probes/s, retrieve 11.6 / 10.5 / 6.1 G rows/s
-                        ///< for 1 / 2 / 4, so 1 stays the default
+  int match_ahead = 1;  ///< retrieve on tables with duplicates: chunks of the probe sequence loaded
+                        ///< together while they stay inside one 128-byte line (1, 2 or 4)
+  int count_ahead = 2;  ///< the same for count. Measured on B200 (profiles/r01_matches_ahead.jsonl,
+                        ///< multiplicity 4) for depth 1 / 2 / 4: count 13.6 / 15.0 / 13.6 G probes/s,
+                        ///< retrieve 11.6 / 10.5 / 6.1 G rows/s - hence 2 and 1
 };
 
 inline tuning_t tuning_from_env()
@@ -98,7 +98,9 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_EXCHANGE_LOOKUP_KPT")) {
     t.exchange_lookup_keys_per_thread = std::atoi(s);
   }
-  if (char const* s = std::getenv("CUCO_B200_MATCH_AHEAD")) { t.match_ahead = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_MATCH_AHEAD")) {
+    t.match_ahead = t.count_ahead = std::atoi(s);  // one switch for sweeps
+  }
   if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
     t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
   }
@@ -481,7 +483,7 @@ class table_engine {
     auto* counter     = this->zeroed_counter(stream);
     auto const grid   = generic_grid(n);
     if (this->fast_path_ok(false)) {
-      with_match_ahead<engine_t>([&](auto ahead) {
+      with_match_ahead<engine_t>(tuning().count_ahead, [&](auto ahead) {
         count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
           <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
       });
@@ -516,7 +518,7 @@ class table_engine {
     auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
       cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
     if (this->fast_path_ok(false)) {
-      with_match_ahead<engine_t>([&](auto ahead) {
+      with_match_ahead<engine_t>(tuning().match_ahead, [&](auto ahead) {
         retrieve_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
           <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
       });
@@ -631,12 +633,12 @@ class table_engine {
 
   /// Look-ahead depth of the all-matches walks: only tables with duplicates have long walks.
   template <typename EngineT, typename Run>
-  static void with_match_ahead(Run&& run)
+  static void with_match_ahead(int depth, Run&& run)
   {
     if constexpr (!EngineT::allows_duplicates) {
       run(std::integral_constant<int, 1>{});
     } else {
-      switch (tuning().match_ahead) {
+      switch (depth) {
         case 4: run(std::integral_constant<int, 4>{}); break;
         case 2: run(std::integral_constant<int, 2>{}); break;
         default: run(std::integral_constant<int, 1>{}); break;

@@ -1,6 +1,10 @@
 #!/bin/bash
 # Round-end validation on the GPU box, every step bounded: full `-m gpu` suite, smoke(), default bench.
 mkdir -p gpurun_out
+timeout 100 tests/_build/dynamic_map_checks_native > gpurun_out/dynamic_map_checks_native.log 2>&1
+echo "dynamic_map_checks_native rc=$?"; tail -3 gpurun_out/dynamic_map_checks_native.log
+timeout 100 oracle/_ref/dynamic_map_checks_ref > gpurun_out/dynamic_map_checks_ref.log 2>&1
+echo "dynamic_map_checks_ref rc=$?"; tail -3 gpurun_out/dynamic_map_checks_ref.log
 timeout 380 python -u -m pytest tests -m gpu -x -q --timeout 150 --timeout-method thread --durations 8 \
   > gpurun_out/pytest_gpu_full.log 2>&1
 echo "pytest_gpu rc=$?"
