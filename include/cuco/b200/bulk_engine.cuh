@@ -75,9 +75,13 @@ struct tuning_t {
   std::size_t l2_window_bytes = std::size_t{48} << 20;
   int match_ahead = 1;  ///< retrieve on tables with duplicates: chunks of the probe sequence loaded
                         ///< together while they stay inside one 128-byte line (1, 2 or 4)
-  int count_ahead = 2;  ///< the same for count. Measured on B200 (profiles/r01_matches_ahead.jsonl,
-                        ///< multiplicity 4) for depth 1 / 2 / 4: count 13.6 / 15.0 / 13.6 G probes/s,
-                        ///< retrieve 11.6 / 10.5 / 6.1 G rows/s - hence 2 and 1
+  int count_ahead = 2;  ///< the same for count, on tables of at least count_ahead_min_table bytes.
+                        ///< Measured on B200 (profiles/r01_matches_ahead*.jsonl, multiplicity 4) for
+                        ///< depth 1 / 2 / 4 on an 800 MB table: count 13.6 / 15.0 / 13.6 G probes/s,
+                        ///< retrieve 11.6 / 10.5 / 6.1 G rows/s; on a 320 MB table depth 2 LOSES
+                        ///< (count 17.7 -> 14.9): the extra registers cost occupancy and a third of
+                        ///< the table already sits in L2
+  std::size_t count_ahead_min_table = std::size_t{512} << 20;
 };
 
 inline tuning_t tuning_from_env()
@@ -99,7 +103,8 @@ inline tuning_t tuning_from_env()
     t.exchange_lookup_keys_per_thread = std::atoi(s);
   }
   if (char const* s = std::getenv("CUCO_B200_MATCH_AHEAD")) {
-    t.match_ahead = t.count_ahead = std::atoi(s);  // one switch for sweeps
+    t.match_ahead = t.count_ahead = std::atoi(s);  // one switch for sweeps, at every table size
+    t.count_ahead_min_table = 0;
   }
   if (char const* s = std::getenv("CUCO_B200_REGION_MIB")) {
     t.region_bytes = static_cast<std::size_t>(std::max(1, std::atoi(s))) << 20;
@@ -483,7 +488,9 @@ class table_engine {
     auto* counter     = this->zeroed_counter(stream);
     auto const grid   = generic_grid(n);
     if (this->fast_path_ok(false)) {
-      with_match_ahead<engine_t>(tuning().count_ahead, [&](auto ahead) {
+      auto const table_bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
+      auto const depth = table_bytes >= tuning().count_ahead_min_table ? tuning().count_ahead : 1;
+      with_match_ahead<engine_t>(depth, [&](auto ahead) {
         count_kernel<IsOuter, block_size, engine_t::sector_chunk_slots, decltype(ahead)::value>
           <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
       });
