@@ -7,8 +7,11 @@
 // Device refs hand out pointers into it (`find` returns a pointer to a real pair), so the layout is
 // part of the surface. What is new here is how it is driven: the fill kernel streams 128-bit stores
 // from a grid sized to the SM count instead of one scalar slot store per thread, and the owning
-// class allocates exactly num_windows windows (the reference over-allocates by a factor of
-// window_size, aow_storage.inl:40).
+// class allocates num_windows windows plus the few it takes to end the allocation on a 32-byte
+// sector boundary (`allocated_windows()`; the reference over-allocates by a factor of window_size,
+// aow_storage.inl:40). The bulk kernels read the table in whole 32-byte sectors, so the sector the
+// last slot lives in must be readable in full whatever allocator the user plugged in; the padding
+// slots are filled with the empty sentinel and are never part of a probe sequence.
 #pragma once
 
 #include <cuco/detail/error.hpp>
@@ -173,9 +176,20 @@ class aow_storage : public detail::aow_storage_base<T, WindowSize, Extent> {
   explicit constexpr aow_storage(Extent size, Allocator const& allocator = {})
     : base_type{size},
       allocator_{allocator},
-      window_deleter_{num_windows(), allocator_},
-      windows_{allocator_.allocate(num_windows()), window_deleter_}
+      window_deleter_{allocated_windows(), allocator_},
+      windows_{allocator_.allocate(allocated_windows()), window_deleter_}
   {
+  }
+
+  /// Windows actually allocated: `num_windows()` rounded up so that the allocation covers the whole
+  /// 32-byte sector holding the last slot (sector-wide table loads never leave the allocation, even
+  /// with a user allocator that sub-allocates tightly).
+  [[nodiscard]] constexpr size_type allocated_windows() const noexcept
+  {
+    constexpr std::size_t sector = 32;
+    auto const bytes  = static_cast<std::size_t>(num_windows()) * sizeof(window_type);
+    auto const padded = (bytes + sector - 1) / sector * sector;
+    return static_cast<size_type>((padded + sizeof(window_type) - 1) / sizeof(window_type));
   }
 
   aow_storage(aow_storage&&)                 = default;
@@ -201,7 +215,9 @@ class aow_storage : public detail::aow_storage_base<T, WindowSize, Extent> {
   /// Sets every slot to `key`, stream-ordered. Pure store bandwidth.
   void initialize_async(value_type key, cuda::stream_ref stream = {}) noexcept
   {
-    auto const num_slots = static_cast<detail::index_type>(this->capacity());
+    // the padding behind the last window is filled too (see allocated_windows())
+    auto const num_slots =
+      static_cast<detail::index_type>(this->allocated_windows()) * detail::index_type{window_size};
     if (num_slots == 0) { return; }
     constexpr int block    = 256;
     constexpr int vec_elems = (16 % sizeof(value_type) == 0) ? 16 / sizeof(value_type) : 1;

@@ -40,6 +40,7 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/type_traits/is_contiguous_iterator.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -186,6 +187,32 @@ inline std::size_t persisting_l2_bytes()
   return bytes;
 }
 
+/// Opts `kernel` into `bytes` of dynamic shared memory on the CURRENT device (the attribute is per
+/// device and per function, so a process driving several GPUs must set it on each; cached per
+/// kernel instantiation and device id). Returns false if the device refuses.
+template <typename Kernel>
+inline bool opt_in_dynamic_smem(Kernel kernel, std::size_t bytes)
+{
+  constexpr int max_devices = 64;
+  static std::atomic<signed char> state[max_devices] = {};  // 0 unknown, 1 ok, -1 refused
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { return false; }
+  if (dev < 0 || dev >= max_devices) {
+    return cudaFuncSetAttribute(
+             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) == cudaSuccess;
+  }
+  auto s = state[dev].load(std::memory_order_relaxed);
+  if (s == 0) {
+    bool const ok = cudaFuncSetAttribute(kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(bytes)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); }
+    s = ok ? 1 : -1;
+    state[dev].store(s, std::memory_order_relaxed);
+  }
+  return s > 0;
+}
+
 template <typename It>
 inline auto unwrap(It it)
 {
@@ -289,8 +316,7 @@ class table_engine {
 
   ~table_engine()
   {
-    if (counter_ != nullptr) { cudaFree(counter_); }
-    if (scratch_ != nullptr) { cudaFree(scratch_); }
+    if (pool_ != nullptr) { cudaMemPoolDestroy(pool_); }
   }
   table_engine(table_engine const&)            = delete;
   table_engine& operator=(table_engine const&) = delete;
@@ -330,7 +356,7 @@ class table_engine {
     if (n == 0) { return 0; }
     auto* counter = this->zeroed_counter(stream);
     this->mutate<true>(first, n, stencil, pred, counter, ref, action_insert{}, stream);
-    return this->read_counter(stream);
+    return this->read_counter(counter, stream);
   }
 
   template <typename InputIt, typename StencilIt, typename Predicate, typename Ref>
@@ -498,7 +524,7 @@ class table_engine {
       count_kernel<IsOuter, block_size, engine_t::window_chunk_slots, 1>
         <<<grid, block_size, 0, stream.get()>>>(in, n, counter, engine);
     }
-    return this->read_counter(stream);
+    return this->read_counter(counter, stream);
   }
 
   /// For every key of [first, last) and every stored element matching it, writes the key to
@@ -533,7 +559,7 @@ class table_engine {
       retrieve_kernel<IsOuter, block_size, engine_t::window_chunk_slots, 1>
         <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
     }
-    return this->read_counter(stream);
+    return this->read_counter(counter, stream);
   }
 
   // ------------------------------------------------------------------------------------------
@@ -552,7 +578,7 @@ class table_engine {
     auto const grid  = static_cast<unsigned>(std::max<cuco::detail::index_type>(
       1, std::min<cuco::detail::index_type>(tiles, cuco::detail::index_type{cuco::detail::multiprocessor_count()} * 8)));
     kernel<<<grid, block_size, 0, stream.get()>>>(engine, counter);
-    return this->read_counter(stream);
+    return this->read_counter(counter, stream);
   }
 
   [[nodiscard]] constexpr auto capacity() const noexcept { return storage_.capacity(); }
@@ -768,8 +794,9 @@ class table_engine {
 
     if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable) {
       if (this->fast_path_ok(true) && this->blocking_pays(n)) {
-        this->blocked_mutate<Counted>(in, n, st, pred, counter, engine, action, stream);
-        return;
+        // false: no scratch memory for the staged batch (or the route kernel could not be
+        // configured) - nothing has been launched yet and the direct path below takes the batch
+        if (this->blocked_mutate<Counted>(in, n, st, pred, counter, engine, action, stream)) { return; }
       }
     }
     if constexpr (engine_t::single_cas && engine_t::pow2_slot) {
@@ -852,17 +879,37 @@ class table_engine {
            static_cast<std::size_t>(n) * 64 >= bytes;
   }
 
-  /// Grow-only staging memory owned by the container (avoids a malloc/free per bulk call).
-  void* scratch(std::size_t bytes)
+  /// Stream-ordered scratch memory for one bulk call (nullptr if the device is out of memory; the
+  /// callers then take a path that needs none). Returned with `scratch_free` on the same stream.
+  [[nodiscard]] void* scratch_alloc(std::size_t bytes, cudaStream_t stream) const noexcept
   {
-    if (bytes > scratch_bytes_) {
-      if (scratch_ != nullptr) { CUCO_CUDA_TRY(cudaFree(scratch_)); }
-      scratch_       = nullptr;
-      scratch_bytes_ = 0;
-      CUCO_CUDA_TRY(cudaMalloc(&scratch_, bytes));
-      scratch_bytes_ = bytes;
+    if (pool_ == nullptr) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess) { return nullptr; }
+      cudaMemPoolProps props{};
+      props.allocType     = cudaMemAllocationTypePinned;
+      props.handleTypes   = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id   = dev;
+      if (cudaMemPoolCreate(&pool_, &props) != cudaSuccess) {
+        cudaGetLastError();
+        pool_ = nullptr;
+        return nullptr;
+      }
+      std::uint64_t keep = ~std::uint64_t{0};
+      cudaMemPoolSetAttribute(pool_, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    return scratch_;
+    void* p = nullptr;
+    if (cudaMallocFromPoolAsync(&p, bytes, pool_, stream) != cudaSuccess) {
+      cudaGetLastError();  // clear the sticky-free error state of the runtime call
+      return nullptr;
+    }
+    return p;
+  }
+
+  void scratch_free(void* p, cudaStream_t stream) const noexcept
+  {
+    if (p != nullptr) { cudaFreeAsync(p, stream); }
   }
 
   /// L2-blocked mutation: route the batch by table region (pass 1), then probe the regions in
@@ -873,7 +920,7 @@ class table_engine {
             typename Predicate,
             typename EngineT,
             typename Action>
-  void blocked_mutate(InputIt in,
+  [[nodiscard]] bool blocked_mutate(InputIt in,
                       cuco::detail::index_type n,
                       StencilIt stencil,
                       Predicate pred,
@@ -894,7 +941,9 @@ class table_engine {
     auto const staged           = static_cast<std::uint64_t>(num_regions) * segment_capacity;
 
     std::size_t const counts_bytes = ((num_regions * sizeof(unsigned int)) + 255) / 256 * 256;
-    auto* base     = static_cast<char*>(this->scratch(counts_bytes + staged * sizeof(value_type)));
+    auto* base = static_cast<char*>(
+      this->scratch_alloc(counts_bytes + staged * sizeof(value_type), stream.get()));
+    if (base == nullptr) { return false; }
     auto* counts   = reinterpret_cast<unsigned int*>(base);
     auto* segments = reinterpret_cast<value_type*>(base + counts_bytes);
     cudaMemsetAsync(counts, 0, num_regions * sizeof(unsigned int), stream.get());
@@ -914,11 +963,10 @@ class table_engine {
                                        EngineT,
                                        Action>;
       constexpr std::size_t smem = route_smem_bytes<route_block_size, value_type>();
-      static bool const configured = [&] {
-        return cudaFuncSetAttribute(
-                 kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
-      }();
-      (void)configured;
+      if (!opt_in_dynamic_smem(kernel, smem)) {
+        this->scratch_free(base, stream.get());
+        return false;
+      }
       auto const tiles =
         cuco::detail::int_div_ceil(n, index_type{route_block_size} * route_items_per_thread);
       auto const grid = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
@@ -959,6 +1007,8 @@ class table_engine {
       run(std::integral_constant<int, 4>{}, std::true_type{});
 #endif
     }
+    this->scratch_free(base, stream.get());
+    return true;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1032,11 +1082,8 @@ class table_engine {
       region_map const regions{static_cast<std::uint64_t>(scaled) + 1, plan.num_regions};
       auto const kernel = exchange_route_kernel<route_block_size, KeysOnly, decltype(in), engine_t>;
       constexpr std::size_t smem = exchange_smem_bytes<route_block_size, elem_type, KeysOnly>();
-      static bool const configured = [&] {
-        return cudaFuncSetAttribute(
-                 kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
-      }();
-      (void)configured;
+      CUCO_EXPECTS(opt_in_dynamic_smem(kernel, smem),
+                   "the device refused the dynamic shared memory the exchange router needs");
       auto const tiles = cuco::detail::int_div_ceil(n, index_type{route_block_size} * route_items_per_thread);
       auto const grid  = static_cast<unsigned>(std::min<index_type>(tiles, index_type{0x7fffffff}));
       kernel<<<grid, route_block_size, smem, stream.get()>>>(in,
@@ -1198,21 +1245,26 @@ class table_engine {
 #endif
   }
 
-  /// Device counter owned by the container, zeroed on `stream`.
+  /// Device counter of ONE bulk call, taken from the stream-ordered pool and zeroed on `stream`.
   size_type* zeroed_counter(cuda::stream_ref stream) const
   {
-    if (counter_ == nullptr) {
-      CUCO_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&counter_), sizeof(size_type)));
-    }
-    CUCO_CUDA_TRY(cudaMemsetAsync(counter_, 0, sizeof(size_type), stream.get()));
-    return counter_;
+    auto* counter = static_cast<size_type*>(this->scratch_alloc(sizeof(size_type), stream.get()));
+    if (counter == nullptr) { CUCO_CUDA_TRY(cudaErrorMemoryAllocation); }
+    CUCO_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(size_type), stream.get()));
+    return counter;
   }
 
-  size_type read_counter(cuda::stream_ref stream) const
+  /// Reads the call's counter back, returns it to the pool and waits for the stream; also the place
+  /// where a failed launch of the synchronous entry points surfaces as cuco::cuda_error.
+  size_type read_counter(size_type* counter, cuda::stream_ref stream) const
   {
     size_type host{};
-    CUCO_CUDA_TRY(
-      cudaMemcpyAsync(&host, counter_, sizeof(size_type), cudaMemcpyDeviceToHost, stream.get()));
+    auto const launched = cudaGetLastError();
+    auto const copied =
+      cudaMemcpyAsync(&host, counter, sizeof(size_type), cudaMemcpyDeviceToHost, stream.get());
+    this->scratch_free(counter, stream.get());
+    CUCO_CUDA_TRY(launched);
+    CUCO_CUDA_TRY(copied);
     stream.wait();
     return host;
   }
@@ -1223,9 +1275,12 @@ class table_engine {
   key_equal predicate_;
   probing_scheme_type probing_scheme_;
   storage_type storage_;
-  mutable size_type* counter_{nullptr};
-  void* scratch_{nullptr};          ///< grow-only staging buffer of the blocked path
-  std::size_t scratch_bytes_{0};
+  /// Stream-ordered pool behind the per-call counter and the staging buffer of the blocked path.
+  /// Every bulk call takes its own allocation ON ITS STREAM and returns it there, so calls on
+  /// different streams never share scratch state (the reference allocates a counter per call too,
+  /// impl.cuh:337-347); the pool keeps freed memory (release threshold = max), so a steady stream of
+  /// calls costs no cudaMalloc after the first.
+  mutable cudaMemPool_t pool_{nullptr};
 };
 
 }  // namespace cuco::b200
