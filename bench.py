@@ -171,6 +171,10 @@ def run_single(args, lib, impl):
     ms_ins, ms_find = sum(t_ins) / len(t_ins), sum(t_find) / len(t_find)
     ms_step = ms_ins + ms_find
     value = 2 * n / (ms_step * 1e-3) / 1e9
+    spread = {"insert_ms_median": statistics.median(t_ins), "insert_ms_best": min(t_ins),
+              "find_ms_median": statistics.median(t_find), "find_ms_best": min(t_find),
+              "value_median": 2 * n / ((statistics.median(t_ins) + statistics.median(t_find)) * 1e-3) / 1e9,
+              "value_best": 2 * n / ((min(t_ins) + min(t_find)) * 1e-3) / 1e9}
 
     # ---- end to end: host pinned buffers in, host results out, copies inside the timed region ----
     h_pairs = torch.empty((n, 2), dtype=torch.int64, pin_memory=True)
@@ -246,11 +250,13 @@ def run_single(args, lib, impl):
     ins_roof = {"bound": "hbm", "kernel": ins_kernel, "achieved": ins_gbs, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": ins_gbs / peak, "traffic": ins_traffic,
                 "algorithmic_bytes_per_op": INSERT_BYTES_PER_OP, "launch_ms": ms_ins}
-    # Dominant single kernel of the step. The find pass is one launch; the blocked insert is two
-    # (route 35 % / probe 65 % of the pass in the ncu launch list, profiles/r01_launches_bench.csv),
-    # so its longest launch is 0.65 * ms_ins.
-    longest_insert_launch = 0.65 * ms_ins if (impl == "native" and blocked) else ms_ins
+    # Dominant single kernel of the step. The find pass is one launch; the blocked insert is two, whose
+    # shares of the pass come from the committed ncu launch list of this command (profiles/launch_shares.json,
+    # written by tools/ncu_table.py from the latest capture), never from a constant in this file.
+    probe_share = launch_share("insert", "probe") if (impl == "native" and blocked) else 1.0
+    longest_insert_launch = probe_share * ms_ins
     dominant, other = (find_roof, ins_roof) if ms_find >= longest_insert_launch else (ins_roof, find_roof)
+    ins_roof["longest_launch_share"] = probe_share
     result = {
         "metric": "Gops/s insert & find (int64 pairs, LF 0.5)",
         "value": value,
@@ -274,44 +280,124 @@ def run_single(args, lib, impl):
         "find_gops": n / (ms_find * 1e-3) / 1e9,
         "insert_ms": ms_ins,
         "find_ms": ms_find,
+        **spread,
         "roofline": dominant,
         "roofline_other_pass": other,
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks.summary(),
     }
-    if args.detail:
-        result["detail"] = run_detail(args, lib, dev)
     table.close()
+    del table, d_pairs, d_keys, h_pairs, h_keys, h_out
+    torch.cuda.empty_cache()
+    # the other points of BASELINE configs[1] (LF 0.8, double_hashing<8>), same protocol, outside the
+    # timed step of the headline configuration
+    if not args.no_points:
+        result["c2_points"] = run_points(args, lib, dev, keys, pairs, out)
     return result
 
 
-def run_detail(args, lib, dev):
-    """Insert/find rates of the other C2 points (LF 0.8, double_hashing<8>) with the same protocol."""
+def launch_share(op: str, launch: str) -> float:
+    """Share of one launch in a multi-launch pass, from the committed ncu launch list."""
+    f = ROOT / "profiles" / "launch_shares.json"
+    try:
+        return float(json.loads(f.read_text())[op][launch])
+    except Exception:
+        return 1.0  # unknown: treat the pass as one launch (never favours the reported fraction)
+
+
+def run_points(args, lib, dev, keys, pairs, out, reps=5):
+    """Insert / find rates (median and best of `reps`, 3 warm-ups) of the C2 points next to the headline
+    one: linear_probing<1> at LF 0.8, double_hashing<8> at LF 0.5 and 0.8 (reference sweep axes:
+    benchmarks/static_map/insert_bench.cu, find_bench.cu)."""
     import cucollections_b200 as cb
     stream = torch.cuda.current_stream(dev)
-    n = args.n
-    keys, pairs = make_inputs(n, dev, seed=42)
-    out = torch.empty(n, dtype=torch.int64, device=dev)
+    n = keys.numel()
     rows = []
-    for probing, cg in (("linear_probing", 1), ("double_hashing", 8)):
-        for lf in (0.5, 0.8):
-            t = cb.static_map(n=n, load_factor=lf, probing=probing, cg_size=cg, device=dev, _library=lib)
-            ins, fnd = [], []
-            for i in range(args.warmup + args.steps):
-                t.clear_async()
-                ei = timed(lambda: t.insert_async(pairs), stream)
-                ef = timed(lambda: t.find(keys, out), stream)
-                torch.cuda.synchronize(dev)
-                if i >= args.warmup:
-                    ins.append(ei[0].elapsed_time(ei[1]))
-                    fnd.append(ef[0].elapsed_time(ef[1]))
-            rows.append({"probing": f"{probing}<{cg}>", "load_factor": lf,
-                         "insert_gops": n / (statistics.median(ins) * 1e-3) / 1e9,
-                         "find_gops": n / (statistics.median(fnd) * 1e-3) / 1e9,
-                         "size": t.size()})
-            t.close()
+    for probing, cg, lf in (("linear_probing", 1, 0.8), ("double_hashing", 8, 0.5), ("double_hashing", 8, 0.8)):
+        t = cb.static_map(n=n, load_factor=lf, probing=probing, cg_size=cg, device=dev, _library=lib)
+        ins, fnd = [], []
+        for i in range(3 + reps):
+            t.clear_async()
+            ei = timed(lambda: t.insert_async(pairs), stream)
+            ef = timed(lambda: t.find(keys, out), stream)
+            torch.cuda.synchronize(dev)
+            if i >= 3:
+                ins.append(ei[0].elapsed_time(ei[1]))
+                fnd.append(ef[0].elapsed_time(ef[1]))
+        ok = bool((out == keys).all().item())
+        rows.append({"probing": f"{probing}<{cg}>", "load_factor": lf, "capacity": t.capacity(),
+                     "insert_gops_median": n / (statistics.median(ins) * 1e-3) / 1e9,
+                     "insert_gops_best": n / (min(ins) * 1e-3) / 1e9,
+                     "find_gops_median": n / (statistics.median(fnd) * 1e-3) / 1e9,
+                     "find_gops_best": n / (min(fnd) * 1e-3) / 1e9,
+                     "insert_frac_of_hbm_roofline": INSERT_BYTES_PER_OP * n / (statistics.median(ins) * 1e-3) / 1e9
+                     / measured_hbm_peak()[0],
+                     "find_frac_of_hbm_roofline": FIND_BYTES_PER_OP * n / (statistics.median(fnd) * 1e-3) / 1e9
+                     / measured_hbm_peak()[0],
+                     "all_found": ok})
+        t.close()
+        del t
+        torch.cuda.empty_cache()
     return rows
+
+
+def multi_gpu_parity_gate(world, rank, dev, lib, routing, n=1_000_000):
+    """Checker leg of the multi-GPU bench (never timed): a partitioned table of n pairs per rank is
+    filled and queried through the SAME routing path as the timed run and compared, bit-exact, with the
+    CPU oracle (oracle/cuco_oracle.c) holding the union of every rank's batch: per-key find / contains
+    on a mixed hit/miss batch of every rank, and the global size(). Raises on any mismatch."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from cucollections_b200 import _cabi
+    from cucollections_b200.partitioned import GpuBackend, partitioned_static_map
+    from oracle import oracle
+
+    gen = torch.Generator(device=dev).manual_seed(977 + rank)
+    keys = torch.randint(1, 3 * n, (n,), generator=gen, device=dev, dtype=torch.int64)  # overlaps across ranks
+    pairs = torch.stack([keys, keys * 5 + 2], dim=1).contiguous()
+    queries = torch.cat([keys[: n // 2], torch.randint(3 * n, 6 * n, (n - n // 2,), generator=gen, device=dev)])
+    table = partitioned_static_map(n * world, 0.5, backend=GpuBackend(dev, lib),
+                                   fused_batch=n if routing != "nccl" else None, routing=routing,
+                                   probing="linear_probing", cg_size=1)
+    table.insert_async(pairs)
+    found, present, size = table.find(queries), table.contains(queries), table.size()
+    table.insert_async(pairs)  # idempotent second pass through the same buffers
+    size_again = table.size()
+    gathered = [torch.empty_like(pairs) for _ in range(world)]
+    dist.all_gather(gathered, pairs)
+    outs = [torch.empty_like(found) for _ in range(world)] if rank == 0 else None
+    dist.gather(found, outs, dst=0)
+    pres = [torch.empty_like(present) for _ in range(world)] if rank == 0 else None
+    dist.gather(present, pres, dst=0)
+    qs = [torch.empty_like(queries) for _ in range(world)] if rank == 0 else None
+    dist.gather(queries, qs, dst=0)
+    verdict = torch.zeros(1, dtype=torch.int64, device=dev)
+    detail = ""
+    if rank == 0:
+        ref = oracle.Table.for_kind(_cabi.MAP_I64_LP1, 2 * n * world, 0.0)
+        for g in gathered:
+            a = g.cpu().numpy()
+            ref.insert(a[:, 0], a[:, 1])
+        bad = []
+        if ref.size() != size or size_again != size:
+            bad.append(f"size {size} / {size_again} != oracle {ref.size()}")
+        for r in range(world):
+            q = qs[r].cpu().numpy()
+            if not np.array_equal(outs[r].cpu().numpy(), ref.find(q)):
+                bad.append(f"find of rank {r}")
+            if not np.array_equal(pres[r].cpu().numpy().astype(bool), ref.contains(q)):
+                bad.append(f"contains of rank {r}")
+        verdict[0] = len(bad)
+        detail = "; ".join(bad)
+    dist.broadcast(verdict, 0)
+    table.close()
+    if int(verdict.item()) != 0:
+        raise AssertionError(f"multi-GPU parity gate failed against the oracle: {detail}")
+    return {"checked_against": "oracle/cuco_oracle.c (CPU restatement) over the union of all ranks' batches",
+            "pairs_per_rank": n, "queries_per_rank": int(queries.numel()), "ops": ["find", "contains", "size"],
+            "size": size, "passed": True}
 
 
 def run_cpu_reference(args):
@@ -336,9 +422,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
-    ap.add_argument("--n", type=int, default=N_KEYS, help="pairs per GPU")
-    ap.add_argument("--detail", action="store_true", help="also time LF 0.8 and double_hashing<8>")
+    ap.add_argument("--n", type=int, default=N_KEYS, help="pairs on one GPU (N = 1)")
+    ap.add_argument("--no-points", action="store_true",
+                    help="skip the LF 0.8 / double_hashing<8> points (c2_points)")
+    ap.add_argument("--total", type=int, default=0,
+                    help="N > 1: pairs over all GPUs (default: BASELINE configs[3], 4 B)")
+    ap.add_argument("--batch", type=int, default=0, help="N > 1: pairs per rank and bulk call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true",
+                    help="N > 1: skip the BASELINE configs[3] leg at its stated size (4 B pairs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -361,7 +453,8 @@ def main():
 
     if world > 1 or args.gpus > 1:
         from cucollections_b200 import partitioned
-        result = partitioned.bench(args, lib, args.impl, clock_sampler=ClockSampler)
+        result = partitioned.bench(args, lib, args.impl, clock_sampler=ClockSampler,
+                                   parity_gate=multi_gpu_parity_gate)
     else:
         result = run_single(args, lib, args.impl)
 

@@ -29,7 +29,8 @@ MAP_I64_DH8_X64 = 9
 MULTISET_I32_DH4_W2 = 10
 MULTISET_I64_LP1_W2 = 11
 MULTIMAP_I64_LP4 = 12
-NUM_KINDS = 13
+MAP_I64_LP1_X64 = 13
+NUM_KINDS = 14
 
 PLUS, MIN, MAX = 0, 1, 2
 
@@ -76,6 +77,7 @@ _PROTOTYPES = {
     "cuco_b200_set_tuning": (_int, [_int, _int, _int, _int, _int, _int, _int]),
     "cuco_b200_set_blocking": (_int, [_int, _int]),
     "cuco_b200_set_blocking_variant": (_int, [_int, _int, _int]),
+    "cuco_b200_set_stream_variant": (_int, [_int, _int, _int]),
     "cuco_b200_partition_count": (_int, [_vp, _int, _int, _i64, _int, _u64, _vp, _vp]),
     "cuco_b200_partition_scatter": (
         _int, [_vp, _vp, _int, _int, _int, _i64, _int, _u64, _vp, _vp, _vp, _vp, _vp]),
@@ -125,7 +127,8 @@ def native() -> Library:
     """The product library (hand-written sm_100a kernels). Raises if it has not been built."""
     global _native
     if _native is None:
-        _native = Library(NATIVE_PATH)
+        # CUCO_B200_LIB: a development build of the same library (cucollections_b200/build.py dev)
+        _native = Library(os.environ.get("CUCO_B200_LIB") or NATIVE_PATH)
     return _native
 
 

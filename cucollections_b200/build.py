@@ -24,7 +24,7 @@ CSRC = ROOT / "cucollections_b200" / "csrc"
 NATIVE_LIB = ROOT / "cucollections_b200" / "libcuco_b200.so"
 REF_LIB = ROOT / "oracle" / "_ref" / "libcuco_ref.so"
 REFERENCE_INCLUDE = Path("/root/reference/include")
-NUM_KINDS = 13
+NUM_KINDS = 14
 # kinds whose launch parameters can be switched at run time (bench / sweep configurations)
 TUNABLE_KINDS = {0, 1, 2, 3}
 
@@ -68,7 +68,8 @@ def _compile(job):
     return obj, time.time() - t0, res.stderr
 
 
-def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], reference: bool, verbose: bool):
+def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], reference: bool, verbose: bool,
+               only_kinds=None):
     build_dir.mkdir(parents=True, exist_ok=True)
     lib.parent.mkdir(parents=True, exist_ok=True)
     # each object depends on its own source, the shared shim header and the header tree it
@@ -82,7 +83,9 @@ def _build_lib(lib: Path, build_dir: Path, include: Path, extra: list[str], refe
     jobs.append((CSRC / "cabi_core.cu", build_dir / "cabi_core.o", base, core_hash))
     for k in range(NUM_KINDS):
         flags = [*base, f"-DCUCO_SHIM_KIND={k}"]
-        if not reference and k in TUNABLE_KINDS:
+        if only_kinds is not None and k not in only_kinds:
+            flags.append("-DCUCO_SHIM_STUB=1")
+        elif not reference and k in TUNABLE_KINDS:
             flags.append("-DCUCO_B200_TUNABLE=1")
         jobs.append((CSRC / "cabi_kind.cu", build_dir / f"cabi_kind_{k}.o", flags, kind_hash))
     jobs = [(s, o, f, hashlib.sha256((h + " ".join(map(str, f)) + " ".join(COMMON)).encode()).hexdigest())
@@ -110,6 +113,14 @@ def build_native(verbose: bool = False) -> Path:
     return _build_lib(NATIVE_LIB, ROOT / "cucollections_b200" / "_build", ROOT / "include", [], False, verbose)
 
 
+def build_dev(kinds, verbose: bool = True) -> Path:
+    """Development build: only `kinds` are real, the others are stubs; written next to the product
+    library as libcuco_b200_dev.so (select it with CUCO_B200_LIB=<path>)."""
+    return _build_lib(ROOT / "cucollections_b200" / "libcuco_b200_dev.so",
+                      ROOT / "cucollections_b200" / "_build_dev", ROOT / "include", [], False, verbose,
+                      only_kinds=set(kinds))
+
+
 def build_reference(verbose: bool = False) -> Path | None:
     """Compiles cuco's own headers behind the same shim into oracle/_ref (dev container only)."""
     if not REFERENCE_INCLUDE.is_dir():
@@ -120,6 +131,9 @@ def build_reference(verbose: bool = False) -> Path | None:
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["native", "reference"]
+    if which and which[0] == "dev":
+        print(build_dev([int(k) for k in which[1:]] or [1]))
+        sys.exit(0)
     if "native" in which:
         print(build_native(verbose=True))
     if "reference" in which:

@@ -46,6 +46,7 @@ KINDS = {
         _Kind(_cabi.MULTISET_I32_DH4_W2, torch.int32, None, "double_hashing", 4, 2, "xxhash_32", True),
         _Kind(_cabi.MULTISET_I64_LP1_W2, torch.int64, None, "linear_probing", 1, 2, "xxhash_32", True),
         _Kind(_cabi.MULTIMAP_I64_LP4, torch.int64, torch.int64, "linear_probing", 4, 1, "xxhash_32", True),
+        _Kind(_cabi.MAP_I64_LP1_X64, torch.int64, torch.int64, "linear_probing", 1, 1, "xxhash_64"),
     )
 }
 

@@ -59,7 +59,7 @@ cuco_shim_factory const g_factories[CUCO_B200_NUM_KINDS] = {
   cuco_shim_make_kind_0, cuco_shim_make_kind_1, cuco_shim_make_kind_2, cuco_shim_make_kind_3,
   cuco_shim_make_kind_4, cuco_shim_make_kind_5, cuco_shim_make_kind_6, cuco_shim_make_kind_7,
   cuco_shim_make_kind_8, cuco_shim_make_kind_9, cuco_shim_make_kind_10, cuco_shim_make_kind_11,
-  cuco_shim_make_kind_12};
+  cuco_shim_make_kind_12, cuco_shim_make_kind_13};
 
 void check_launch()
 {
@@ -860,6 +860,20 @@ int cuco_b200_set_blocking_variant(int keys_per_thread, int cas_first, int prefe
   }
   if (cas_first >= 0) { t.blocked_cas_first = cas_first != 0; }
   if (prefetch >= 0) { t.blocked_prefetch = prefetch != 0; }
+  return 0;
+#endif
+}
+
+int cuco_b200_set_stream_variant(int tile_route, int stream_probe, int slots)
+{
+#if defined(CUCO_SHIM_REFERENCE)
+  (void)tile_route, (void)stream_probe, (void)slots;
+  return 1;
+#else
+  auto& t = cuco::b200::tuning();
+  if (tile_route >= 0) { t.blocked_tile_route = tile_route != 0; }
+  if (stream_probe >= 0) { t.blocked_stream_probe = stream_probe != 0; }
+  if (slots == 1 || slots == 2) { t.stream_slots = slots; }
   return 0;
 #endif
 }

@@ -5,6 +5,19 @@
 // public container API is used, so both compile from this one source.
 #include "cabi_table.hpp"
 
+#if defined(CUCO_SHIM_STUB)
+// Development builds (cucollections_b200/build.py, CUCO_B200_DEV_KINDS) compile only the kinds under
+// work; the others get this stub so that the library still links and says why a kind is missing.
+#include <stdexcept>
+#define CUCO_SHIM_CAT2(a, b) a##b
+#define CUCO_SHIM_CAT(a, b)  CUCO_SHIM_CAT2(a, b)
+cuco_b200_table* CUCO_SHIM_CAT(cuco_shim_make_kind_, CUCO_SHIM_KIND)(
+  std::int64_t, double, std::int64_t, std::int64_t, int, std::int64_t, void*)
+{
+  throw std::invalid_argument("this kind is not part of the development build of the library");
+}
+#else
+
 #include <cuco/static_map.cuh>
 #include <cuco/static_multimap.cuh>
 #include <cuco/static_multiset.cuh>
@@ -98,6 +111,8 @@ using container_t = multiset_t<i32, cuco::double_hashing<4, cuco::default_hash_f
 using container_t = multiset_t<i64, cuco::linear_probing<1, cuco::default_hash_function<i64>>, 2>;
 #elif CUCO_SHIM_KIND == 12
 using container_t = multimap_t<i64, i64, cuco::linear_probing<4, cuco::default_hash_function<i64>>, 1>;
+#elif CUCO_SHIM_KIND == 13
+using container_t = map_t<i64, i64, cuco::linear_probing<1, cuco::xxhash_64<i64>>, 1>;
 #else
 #error "unknown CUCO_SHIM_KIND"
 #endif
@@ -335,7 +350,7 @@ class table_impl final : public cuco_b200_table {
   }
 
   // ---- exchange path (no reference counterpart: our engine only) ----------------------------
-#if defined(CUCO_SHIM_REFERENCE) || (CUCO_SHIM_KIND >= 10)
+#if defined(CUCO_SHIM_REFERENCE) || (CUCO_SHIM_KIND >= 10 && CUCO_SHIM_KIND <= 12)
   exchange_shape exchange_plan(i64, int) override { throw unsupported(); }
   void exchange_route(const void*, const void*, i64, bool, exchange_shape, int, int, std::uint64_t,
                       void* const*, void* const*, void* const*, void*, void*, void*, void*, void*,
@@ -518,3 +533,4 @@ cuco_b200_table* CUCO_SHIM_CAT(cuco_shim_make_kind_, CUCO_SHIM_KIND)(std::int64_
 {
   return new table_impl<selected_container>(size, load_factor, empty_key, empty_value, has_erased, erased_key, stream);
 }
+#endif  // CUCO_SHIM_STUB

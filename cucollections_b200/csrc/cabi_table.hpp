@@ -78,3 +78,4 @@ CUCO_SHIM_DECLARE_FACTORY(9);
 CUCO_SHIM_DECLARE_FACTORY(10);
 CUCO_SHIM_DECLARE_FACTORY(11);
 CUCO_SHIM_DECLARE_FACTORY(12);
+CUCO_SHIM_DECLARE_FACTORY(13);

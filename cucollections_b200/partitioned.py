@@ -35,6 +35,7 @@ from . import _cabi
 from .containers import static_map
 
 DEFAULT_SALT = 0x9E3779B97F4A7C15
+DEFAULT_ROUTING = "fused"  # "staged" | "fused" | "nccl"; CUCO_B200_ROUTING overrides
 
 
 def _vp(t):
@@ -154,6 +155,10 @@ class FusedExchange:
         self.trace = [] if os.environ.get("CUCO_B200_EXCHANGE_TRACE") else None
         torch.cuda.synchronize(self.device)
         dist.barrier(group)
+
+    def launches_per_step(self) -> int:
+        # insert = route + publish + probe; find = route + publish + lookup + unpermute (per lane)
+        return 7 * self.K
 
     def _mark(self, label):
         if self.trace is not None:
@@ -290,7 +295,7 @@ class partitioned_static_map:
     """static_map<int64,int64> sharded over the ranks of `group` by owner(key)."""
 
     def __init__(self, n_total, load_factor=0.5, *, backend, group=None, salt=DEFAULT_SALT,
-                 headroom=1.03, fused_batch=None, fused_lanes=None, **table_kw):
+                 headroom=1.03, fused_batch=None, fused_lanes=None, routing=None, **table_kw):
         """`fused_batch`: largest batch (elements per rank and call) the fused exchange path is sized
         for; None keeps the all_to_all routing (also the fallback for spilled elements).
         `fused_lanes`: chunks per batch that are software-pipelined (routing of chunk c+1 overlaps the
@@ -305,9 +310,23 @@ class partitioned_static_map:
         n_local = int(-(-n_total // self.world) * headroom) + 1
         self.table = backend.make_table(n_local, load_factor, **table_kw)
         self.fused = None
+        self.routing = "nccl"
         if fused_batch:
-            lanes = fused_lanes or int(os.environ.get("CUCO_B200_EXCHANGE_LANES", "1"))
-            self.fused = FusedExchange(self.table, fused_batch, group, backend.device, salt, lanes=lanes)
+            self.routing = routing or os.environ.get("CUCO_B200_ROUTING", DEFAULT_ROUTING)
+            if self.routing == "nccl":
+                pass
+            elif self.routing == "staged":
+                self.fused = StagedExchange(self.table, fused_batch, group, backend.device, salt)
+            else:
+                lanes = fused_lanes or int(os.environ.get("CUCO_B200_EXCHANGE_LANES", "1"))
+                self.fused = FusedExchange(self.table, fused_batch, group, backend.device, salt, lanes=lanes)
+
+    def launches_per_step(self) -> int:
+        """Kernels of this repository per (insert + find) step and rank, for bench.py's `gpu_launches`."""
+        if self.fused is not None:
+            return self.fused.launches_per_step()
+        # all_to_all routing: 2 x (count + scatter) + insert (route + probe when blocked) + find + scatter_by_index
+        return 8
 
     # ---- exchange helpers ------------------------------------------------------------------------
     def _exchange_counts(self, send_counts):
@@ -419,7 +438,125 @@ def _hbm_peak():
         return 6650.0
 
 
-def bench(args, lib, impl, clock_sampler=None):
+def _timed_pass(table, dev, stream, steps, warmup, pairs, keys, out):
+    """warmup + steps of (clear, insert, find); returns per-step (insert ms, find ms) lists."""
+    def step():
+        table.clear_async()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record(stream)
+        table.insert_async(pairs)
+        b.record(stream)
+        table.find(keys, out)
+        c.record(stream)
+        return a, b, c
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    assert bool((out == keys).all().item()), "partitioned find returned a wrong payload"
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    events = [step() for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    return [a.elapsed_time(b) for a, b, _ in events], [b.elapsed_time(c) for _, b, c in events]
+
+
+def _max_over_ranks(values, dev):
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def _c4_leg(args, lib, dev, rank, world, routing):
+    """BASELINE configs[3] at its stated size: `total` pairs (default 4 B) over the `world` GPUs, LF 0.5,
+    linear_probing<1, xxhash_64> (a 32-bit hash folds unevenly onto shards of 1 - 4 G slots). Every rank
+    feeds its share in batches of `batch` pairs (keys of batch b are regenerated from its seed for the
+    find pass instead of being kept: at 2 GPUs a rank's 2 G pairs are 32 GB next to a 64 GB shard).
+    Events around the bulk calls only, max over ranks per batch, summed. Properties checked at this size:
+    every key found with its own payload, absent keys miss, global size == number of distinct keys."""
+    from . import key_generator as kg
+
+    stream = torch.cuda.current_stream(dev)
+    total = args.total or 4_000_000_000
+    share = total // world
+    batch = min(args.batch or 500_000_000, share)
+    batches = -(-share // batch)
+    table = partitioned_static_map(total, 0.5, backend=GpuBackend(dev, lib),
+                                   fused_batch=batch if routing != "nccl" else None, routing=routing,
+                                   probing="linear_probing", cg_size=1, hash="xxhash_64")
+    out = torch.empty(batch, dtype=torch.int64, device=dev)
+
+    def make(b):
+        m = min(batch, share - b * batch)
+        # rank r draws uniformly from its own value range [r * share + 1, (r + 1) * share] (~63 % distinct)
+        g = torch.Generator(device=dev).manual_seed(1000 + 64 * b + rank)
+        k = torch.randint(1 + rank * share, 1 + (rank + 1) * share, (m,), generator=g, device=dev, dtype=torch.int64)
+        return k, torch.stack([k, k], dim=1).contiguous()
+
+    ins_ms, find_ms = [], []
+    seen = torch.zeros(share, dtype=torch.bool, device=dev)  # exact distinct count without a sort
+    for b in range(batches):
+        keys, pairs = make(b)
+        for _ in range(1 if b else 2):  # one untimed warm-up of the path on the first batch
+            if not b:
+                table.clear_async()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            table.insert_async(pairs)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+        ins_ms.append(e0.elapsed_time(e1))
+        del pairs
+        seen[keys - (1 + rank * share)] = True
+        del keys
+    distinct = int(seen.sum().item())
+    del seen
+    torch.cuda.empty_cache()
+    size = table.size()
+    ok = True
+    for b in range(batches):
+        keys, _ = make(b)
+        del _
+        o = out[: keys.numel()]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        table.find(keys, o)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        find_ms.append(e0.elapsed_time(e1))
+        ok = ok and bool((o == keys).all().item())
+        if b == 0:
+            absent = keys[: 1 << 20] + total + 7
+            ok = ok and bool((table.find(absent) == -1).all().item())
+        del keys
+    ins = _max_over_ranks(ins_ms, dev)
+    fnd = _max_over_ranks(find_ms, dev)
+    counts = torch.tensor([distinct, 0 if ok else 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(counts)
+    capacity = table.table.capacity()
+    table.close()
+    torch.cuda.empty_cache()
+    t_ins, t_find = sum(ins) * 1e-3, sum(fnd) * 1e-3
+    pairs_done = share * world
+    result = {
+        "workload": f"hash-partitioned static_map<int64,int64>, {pairs_done} uniform pairs over {world} GPUs "
+                    f"({share} per GPU in {batches} bulk calls of {batch}), LF 0.5, linear_probing<1, xxhash_64>",
+        "pairs_total": pairs_done, "pairs_per_gpu": share, "batch": batch, "shard_capacity": capacity,
+        "shard_bytes": capacity * 16,
+        "insert_gops": pairs_done / t_ins / 1e9, "find_gops": pairs_done / t_find / 1e9,
+        "value": 2 * pairs_done / (t_ins + t_find) / 1e9, "unit": "Gops/s",
+        "insert_ms_per_batch": ins, "find_ms_per_batch": fnd,
+        "size": size, "distinct_keys": int(counts[0].item()),
+        "properties": {"all_found_with_own_payload_and_absent_miss": int(counts[1].item()) == 0,
+                       "size_equals_distinct": size == int(counts[0].item())},
+    }
+    if not all(result["properties"].values()):
+        raise AssertionError(f"C4 leg failed its properties: {result}")
+    return result
+
+
+def bench(args, lib, impl, clock_sampler=None, parity_gate=None):
     import json  # noqa: F401
     import os
 
@@ -433,47 +570,34 @@ def bench(args, lib, impl, clock_sampler=None):
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream(dev)
+    routing = os.environ.get("CUCO_B200_ROUTING", DEFAULT_ROUTING if impl == "native" else "nccl")
+
+    # ---- checker leg: the same routing path against the CPU oracle, before anything is timed ----
+    parity = parity_gate(world, rank, dev, lib, routing) if parity_gate is not None else None
 
     n = args.n  # pairs per rank: weak scaling
     # rank r owns the value range [r*n, (r+1)*n) of the global uniform stream (fixed seeds)
     keys = kg.uniform(n, 1, torch.int64, dev, seed=42 + rank) + rank * n
     pairs = torch.stack([keys, keys], dim=1).contiguous()
     out = torch.empty(n, dtype=torch.int64, device=dev)
-    routing = os.environ.get("CUCO_B200_ROUTING", "fused" if impl == "native" else "nccl")
     table = partitioned_static_map(n * world, 0.5, backend=GpuBackend(dev, lib),
-                                   fused_batch=n if routing == "fused" else None,
+                                   fused_batch=n if routing != "nccl" else None, routing=routing,
                                    probing="linear_probing", cg_size=1)
 
-    def step():
-        table.clear_async()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record(stream)
-        table.insert_async(pairs)
-        b.record(stream)
-        table.find(keys, out)
-        c.record(stream)
-        return a, b, c
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize(dev)
-    assert bool((out == keys).all().item()), "partitioned find returned a wrong payload"
-    dist.barrier()
-    torch.cuda.synchronize(dev)
     sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
     if sampler is not None:
         sampler.__enter__()
-    events = [step() for _ in range(args.steps)]
-    torch.cuda.synchronize(dev)
+    t_ins, t_find = _timed_pass(table, dev, stream, args.steps, args.warmup, pairs, keys, out)
     if sampler is not None:
         sampler.__exit__(None, None, None)
-    dist.barrier()
-    ins = statistics.mean(a.elapsed_time(b) for a, b, _ in events)
-    fnd = statistics.mean(b.elapsed_time(c) for _, b, c in events)
-    t = torch.tensor([ins, fnd, ins + fnd], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ins, fnd, total = t.tolist()
+    mean = lambda v: sum(v) / len(v)  # noqa: E731
+    ins, fnd, total = _max_over_ranks([mean(t_ins), mean(t_find), mean(t_ins) + mean(t_find)], dev)
+    ins_med, fnd_med, ins_best, fnd_best = _max_over_ranks(
+        [statistics.median(t_ins), statistics.median(t_find), min(t_ins), min(t_find)], dev)
     total_size = table.size()
+    distinct = torch.tensor([int(torch.unique(keys).numel())], dtype=torch.int64, device=dev)
+    dist.all_reduce(distinct)  # the ranks' value ranges are disjoint
+    assert total_size == int(distinct.item()), "global size() != number of distinct keys"
 
     # end to end: pinned host buffers in, host results out
     h_pairs = torch.empty((n, 2), dtype=torch.int64, pin_memory=True).copy_(pairs)
@@ -498,11 +622,13 @@ def bench(args, lib, impl, clock_sampler=None):
     dist.barrier()
     ev = [e2e_step() for _ in range(max(1, min(args.steps, 3)))]
     torch.cuda.synchronize(dev)
-    e2e_ms = torch.tensor([statistics.mean(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64,
-                          device=dev)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
+    assert bool((h_out == h_keys).all().item()), "end-to-end partitioned find returned a wrong payload"
+    e2e_ms = _max_over_ranks([statistics.mean(a.elapsed_time(b) for a, b in ev)], dev)[0]
     ops = 2 * n * world
+    described = {"staged": "staged exchange: local grouping by (owner, table slice), copy-engine transfers over "
+                           "NVLink overlapped slice by slice with the owners' L2-blocked probe",
+                 "fused": "fused P2P routing over NVLink (one partition kernel stores into the owners' memory)",
+                 "nccl": "NCCL all-to-all routing"}[routing]
     result = {
         "metric": "Gops/s insert & find (int64 pairs, LF 0.5)",
         "value": ops / (total * 1e-3) / 1e9,
@@ -518,21 +644,26 @@ def bench(args, lib, impl, clock_sampler=None):
         "data": "synthetic",
         "impl": impl,
         "config": {"workload": f"hash-partitioned static_map<int64,int64>, {n} uniform pairs per GPU "
-                               f"insert + find, LF 0.5, linear_probing<1>, {world} GPUs, "
-                               + ("fused P2P routing over NVLink (one partition kernel stores into the owners' memory)"
-                                  if routing == "fused" else "NCCL all-to-all routing"),
+                               f"insert + find, LF 0.5, linear_probing<1>, {world} GPUs, " + described,
                    "n_per_gpu": n, "total_size": total_size,
-                   "timing": "CUDA events per rank around partition + all-to-all + local kernels, "
+                   "timing": "CUDA events per rank around routing + exchange + local kernels, "
                              "max over ranks; clear outside; working sets larger than L2"},
         "insert_gops": n * world / (ins * 1e-3) / 1e9,
         "find_gops": n * world / (fnd * 1e-3) / 1e9,
         "insert_ms": ins,
         "find_ms": fnd,
+        "insert_ms_median": ins_med, "find_ms_median": fnd_med,
+        "insert_ms_best": ins_best, "find_ms_best": fnd_best,
+        "value_median": ops / ((ins_med + fnd_med) * 1e-3) / 1e9,
+        "value_best": ops / ((ins_best + fnd_best) * 1e-3) / 1e9,
+        "parity": parity,
         # per GPU the insert moves the single-GPU algorithmic bytes (80 B/op) through HBM and
         # 16 B * (P-1)/P per pair through NVLink; report the HBM view (same definition as N=1) and
         # the NVLink egress next to it
-        "roofline": {"bound": "hbm", "kernel": "insert (exchange_route_kernel + blocked_mutate_kernel)"
-                     if routing == "fused" else "insert (partition + all_to_all + local insert)",
+        "roofline": {"bound": "hbm", "kernel": {"staged": "insert (exchange_route_kernel -> copy engines -> "
+                                                          "tile_route_kernel + blocked_mutate_kernel per slice)",
+                                                "fused": "insert (exchange_route_kernel + blocked_mutate_kernel)",
+                                                "nccl": "insert (partition + all_to_all + local insert)"}[routing],
                      "achieved": 80.0 * n / (ins * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s",
                      "frac": 80.0 * n / (ins * 1e-3) / 1e9 / _hbm_peak(), "traffic": None,
                      "per_gpu": True,
@@ -541,17 +672,26 @@ def bench(args, lib, impl, clock_sampler=None):
         "e2e": {"value": ops / (e2e_ms * 1e-3) / 1e9, "unit": "Gops/s",
                 "h2d_bytes_per_step": int(n * 24 * world), "d2h_bytes_per_step": int(n * 8 * world),
                 "ms_per_step": e2e_ms},
-        # our kernels per step and rank. fused: insert = route + publish + probe, find = route +
-        # publish + lookup + unpermute; all_to_all routing: 2 x (count + scatter) + insert (route +
-        # probe when blocked) + find + scatter_by_index
-        "gpu_launches": (7 if routing == "fused" else 8) * args.steps * world,
+        "gpu_launches": table.launches_per_step() * args.steps * world,
         "clocks": (sampler.summary() if sampler is not None else
                    {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}),
     }
-    if table.fused is not None and table.fused.trace is not None:
+    if impl != "native":
+        # cuco has no multi-GPU path: this arm is cuco's own local table behind THIS repository's partition
+        # kernels and an NCCL all-to-all. It is a constructed baseline, not a reference measurement.
+        result["reference_class"] = "constructed"
+        result["config"]["reference_note"] = ("cuCollections is single-GPU; this arm = repo partition kernels + "
+                                              "NCCL all_to_all_single + cuco's local static_map per rank")
+    if table.fused is not None and getattr(table.fused, "trace", None) is not None:
         traces = [None] * world
         dist.all_gather_object(traces, table.fused.trace_summary())
         result["exchange_trace_ms"] = traces  # one dict per rank
     table.close()
+    del table, pairs, keys, out, h_pairs, h_keys, h_out, d_pairs, d_keys
+    torch.cuda.empty_cache()
+    dist.barrier()
+    if impl == "native" and not getattr(args, "no_c4", False):
+        result["c4"] = _c4_leg(args, lib, dev, rank, world, routing)
+        result["config"]["c4_workload"] = result["c4"]["workload"]
     dist.barrier()
     return result

@@ -27,6 +27,7 @@
 #include <cuco/b200/bulk_kernels.cuh>
 #include <cuco/b200/match_kernels.cuh>
 #include <cuco/b200/probe_engine.cuh>
+#include <cuco/b200/stream_kernels.cuh>
 #include <cuco/detail/error.hpp>
 #include <cuco/detail/utility/cuda.hpp>
 #include <cuco/detail/utils.hpp>
@@ -40,13 +41,15 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/type_traits/is_contiguous_iterator.h>
 
-#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 namespace cuco::b200 {
 
@@ -72,6 +75,13 @@ struct tuning_t {
   bool blocked_cas_first      = true;   ///< pass 2 starts with the CAS (table slice is L2-resident;
                                         ///< measured 34.9 vs 30.6 Gops/s, profiles/r01_insert_probe_v4.jsonl)
   bool blocked_prefetch       = true;   ///< pass 2 streams the next region into L2 ahead of use
+  bool blocked_tile_route     = true;   ///< pass 1 = tile_route_kernel (bulk-copy input, persistent) when
+                                        ///< the batch is a 16-byte aligned array of slot images
+  bool blocked_stream_probe   = false;  ///< pass 2 = stream_mutate_kernel (warp-persistent, refilling); measured
+                                        ///< SLOWER than blocked_mutate_kernel on B200 (5.1 vs 2.6 ms per 100 M,
+                                        ///< profiles/r02_insert_lab_v2_rows_parked.jsonl): kept for sweeps only
+  int stream_slots            = 2;      ///< rows of 32 keys in flight per warp of stream_mutate_kernel (1, 2)
+  bool stream_scout           = true;   ///< every key's home line is prefetched into L2 one chunk ahead of its CAS
   int exchange_lookup_keys_per_thread = 2;  ///< owner side of routed lookups (1, 2 or 4)
   std::size_t l2_window_bytes = std::size_t{48} << 20;
   int match_ahead = 1;  ///< retrieve on tables with duplicates: chunks of the probe sequence loaded
@@ -100,6 +110,10 @@ inline tuning_t tuning_from_env()
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_KPT")) { t.blocked_keys_per_thread = std::atoi(s); }
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_CAS_FIRST")) { t.blocked_cas_first = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_BLOCKED_PREFETCH")) { t.blocked_prefetch = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_TILE_ROUTE")) { t.blocked_tile_route = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_STREAM_PROBE")) { t.blocked_stream_probe = std::atoi(s) != 0; }
+  if (char const* s = std::getenv("CUCO_B200_STREAM_SLOTS")) { t.stream_slots = std::atoi(s); }
+  if (char const* s = std::getenv("CUCO_B200_STREAM_SCOUT")) { t.stream_scout = std::atoi(s) != 0; }
   if (char const* s = std::getenv("CUCO_B200_EXCHANGE_LOOKUP_KPT")) {
     t.exchange_lookup_keys_per_thread = std::atoi(s);
   }
@@ -188,29 +202,26 @@ inline std::size_t persisting_l2_bytes()
 }
 
 /// Opts `kernel` into `bytes` of dynamic shared memory on the CURRENT device (the attribute is per
-/// device and per function, so a process driving several GPUs must set it on each; cached per
-/// kernel instantiation and device id). Returns false if the device refuses.
+/// device and per function, so a process driving several GPUs must set it on each). Cached per
+/// (kernel address, device); kernels of different instantiations may share one C++ type, so the
+/// cache is keyed by the pointer value, never by the type. Returns false if the device refuses.
 template <typename Kernel>
 inline bool opt_in_dynamic_smem(Kernel kernel, std::size_t bytes)
 {
-  constexpr int max_devices = 64;
-  static std::atomic<signed char> state[max_devices] = {};  // 0 unknown, 1 ok, -1 refused
+  static std::mutex guard;
+  static std::map<std::pair<void const*, int>, bool> done;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { return false; }
-  if (dev < 0 || dev >= max_devices) {
-    return cudaFuncSetAttribute(
-             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) == cudaSuccess;
-  }
-  auto s = state[dev].load(std::memory_order_relaxed);
-  if (s == 0) {
-    bool const ok = cudaFuncSetAttribute(kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(bytes)) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); }
-    s = ok ? 1 : -1;
-    state[dev].store(s, std::memory_order_relaxed);
-  }
-  return s > 0;
+  auto const key = std::make_pair(reinterpret_cast<void const*>(kernel), dev);
+  std::lock_guard<std::mutex> lock{guard};
+  auto const it = done.find(key);
+  if (it != done.end()) { return it->second; }
+  bool const ok = cudaFuncSetAttribute(kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(bytes)) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); }
+  done.emplace(key, ok);
+  return ok;
 }
 
 template <typename It>
@@ -218,6 +229,34 @@ inline auto unwrap(It it)
 {
   return thrust::try_unwrap_contiguous_iterator(it);
 }
+
+/// Key type of an input element: the element itself for sets; `first` / `get<0>` of a pair-like for
+/// maps (host-side mirror of probe_engine::heterogeneous_value + key_of).
+template <typename T, typename = void>
+struct has_member_first : std::false_type {};
+template <typename T>
+struct has_member_first<T, std::void_t<decltype(std::declval<T const&>().first)>> : std::true_type {};
+
+template <typename T>
+struct type_box {
+  using type = T;
+};
+
+template <typename T, bool HasPayload>
+struct input_key_of {
+  static auto probe()
+  {
+    if constexpr (!HasPayload) {
+      return type_box<cuda::std::remove_cv_t<T>>{};
+    } else if constexpr (has_member_first<T>::value) {
+      return type_box<
+        cuda::std::remove_cv_t<cuda::std::remove_reference_t<decltype(std::declval<T const&>().first)>>>{};
+    } else {
+      return type_box<cuda::std::remove_cv_t<cuda::std::tuple_element_t<0, T>>>{};
+    }
+  }
+  using type = typename decltype(probe())::type;
+};
 
 template <class Key,
           class Value,
@@ -789,16 +828,43 @@ class table_engine {
     auto st           = unwrap(stencil);
     auto const engine = ref.engine();
     using engine_t    = std::decay_t<decltype(engine)>;
-    void* base        = storage_.data();
-    auto const window = this->window_bytes();
 
-    if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable) {
+    // The blocked path stages slot images and probes with the STORED key, so it is only taken when
+    // the batch's key type is the table's key type: a heterogeneous insert key must be hashed and
+    // compared in its own type (reference open_addressing_ref_impl.cuh:1506-1521), which only the
+    // direct kernels do.
+    using input_value_type = typename cuda::std::iterator_traits<decltype(in)>::value_type;
+    constexpr bool native_keys =
+      std::is_same_v<typename input_key_of<input_value_type, has_payload>::type, key_type>;
+    if constexpr (engine_t::single_cas && engine_t::pow2_slot && Action::blockable && native_keys) {
       if (this->fast_path_ok(true) && this->blocking_pays(n)) {
         // false: no scratch memory for the staged batch (or the route kernel could not be
         // configured) - nothing has been launched yet and the direct path below takes the batch
         if (this->blocked_mutate<Counted>(in, n, st, pred, counter, engine, action, stream)) { return; }
       }
     }
+    this->direct_mutate<Counted>(in, n, st, pred, counter, engine, action, stream);
+  }
+
+  /// The un-regrouped mutation kernels: thread-per-key fast path, else the general fallback.
+  template <bool Counted,
+            typename InputIt,
+            typename StencilIt,
+            typename Predicate,
+            typename EngineT,
+            typename Action>
+  void direct_mutate(InputIt in,
+                     cuco::detail::index_type n,
+                     StencilIt st,
+                     Predicate pred,
+                     size_type* counter,
+                     EngineT const& engine,
+                     Action action,
+                     cuda::stream_ref stream) noexcept
+  {
+    using engine_t    = EngineT;
+    void* base        = storage_.data();
+    auto const window = this->window_bytes();
     if constexpr (engine_t::single_cas && engine_t::pow2_slot) {
       if (this->fast_path_ok(true)) {
         auto run = [&](auto kpt, auto chunk) {
@@ -814,8 +880,8 @@ class table_engine {
                                               CasFirst,
                                               Counted,
                                               Policy,
-                                              decltype(in),
-                                              decltype(st),
+                                              InputIt,
+                                              StencilIt,
                                               Predicate,
                                               size_type,
                                               engine_t,
@@ -855,8 +921,8 @@ class table_engine {
     }
     auto const kernel = generic_mutate_kernel<block_size,
                                               Counted,
-                                              decltype(in),
-                                              decltype(st),
+                                              InputIt,
+                                              StencilIt,
                                               Predicate,
                                               size_type,
                                               engine_t,
@@ -871,9 +937,10 @@ class table_engine {
   {
     auto const& t = tuning();
     if (t.blocked == 0 || n <= 0) { return false; }
-    if (n >= (cuco::detail::index_type{1} << 32)) { return false; }  // segment counters are 32-bit
     auto const bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
-    if (bytes / route_max_regions > (std::size_t{48} << 20)) { return false; }
+    // at most route_max_regions regions, and a region must stay L2-resident while it is probed
+    // (measured: 64 MiB windows still run at 0.8x the rate of 16 MiB ones, profiles/r01_hardware_probes.md)
+    if (bytes / route_max_regions > (std::size_t{64} << 20)) { return false; }
     if (t.blocked > 0) { return true; }
     return bytes >= t.blocked_min_table && n >= t.blocked_min_elements &&
            static_cast<std::size_t>(n) * 64 >= bytes;
@@ -930,14 +997,29 @@ class table_engine {
                       cuda::stream_ref stream)
   {
     using cuco::detail::index_type;
+    // region counters and staged positions are 32-bit: larger batches go through in slices
+    constexpr index_type slice = index_type{1} << 31;
+    if (n > slice) {
+      for (index_type done = 0; done < n; done += slice) {
+        auto const len = std::min<index_type>(slice, n - done);
+        if (!this->blocked_mutate<Counted>(in + done, len, stencil + done, pred, counter, engine, action, stream)) {
+          if (done == 0) { return false; }
+          // later slices without scratch memory: the direct kernel takes them (same results)
+          this->direct_mutate<Counted>(in + done, n - done, stencil + done, pred, counter, engine, action, stream);
+          return true;
+        }
+      }
+      return true;
+    }
     auto const& t          = tuning();
     auto const capacity    = static_cast<std::uint64_t>(storage_.capacity());
     auto const table_bytes = capacity * sizeof(value_type);
     auto const num_regions = static_cast<std::uint32_t>(std::min<std::uint64_t>(
       route_max_regions, std::max<std::uint64_t>(2, (table_bytes + t.region_bytes - 1) / t.region_bytes)));
-    // expected elements per region plus 1/16 slack and a constant for tiny batches
+    // expected elements per region plus 1/16 slack and a constant for tiny batches; a multiple of
+    // 16 elements so that every segment (and every 128-key chunk of it) starts 16-byte aligned
     auto const mean             = (static_cast<std::uint64_t>(n) + num_regions - 1) / num_regions;
-    auto const segment_capacity = static_cast<std::uint32_t>(mean + mean / 16 + 1024);
+    auto const segment_capacity = static_cast<std::uint32_t>((mean + mean / 16 + 1024 + 15) / 16 * 16);
     auto const staged           = static_cast<std::uint64_t>(num_regions) * segment_capacity;
 
     std::size_t const counts_bytes = ((num_regions * sizeof(unsigned int)) + 255) / 256 * 256;
@@ -952,7 +1034,38 @@ class table_engine {
     region_map const regions{static_cast<std::uint64_t>(scaled) + 1, num_regions};
 
     constexpr int chunk = EngineT::sector_chunk_slots;
-    {
+    // ---- pass 1 ----
+    bool routed = false;
+    if constexpr (std::is_pointer_v<InputIt>) {
+      using input_value = std::remove_cv_t<std::remove_pointer_t<InputIt>>;
+      if constexpr (std::is_same_v<input_value, value_type>) {
+        if (t.blocked_tile_route && (reinterpret_cast<std::uintptr_t>(in) % 16) == 0) {
+          auto const kernel = tile_route_kernel<tile_route_block_size,
+                                                chunk,
+                                                Counted,
+                                                StencilIt,
+                                                Predicate,
+                                                size_type,
+                                                EngineT,
+                                                Action>;
+          auto const smem = tile_route_smem_bytes<tile_route_block_size, value_type>(num_regions);
+          if (opt_in_dynamic_smem(kernel, std::size_t{200} << 10)) {
+            auto const tiles =
+              cuco::detail::int_div_ceil(n, index_type{tile_route_block_size} * route_items_per_thread);
+            static int const resident = [&] {
+              int per_sm = 0;
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile_route_block_size, smem);
+              return std::max(1, per_sm) * cuco::detail::multiprocessor_count();
+            }();
+            auto const grid = static_cast<unsigned>(std::min<index_type>(tiles, resident));
+            kernel<<<grid, tile_route_block_size, smem, stream.get()>>>(
+              in, n, stencil, pred, segments, counts, regions, segment_capacity, counter, engine, action);
+            routed = true;
+          }
+        }
+      }
+    }
+    if (!routed) {
       auto const kernel = route_kernel<route_block_size,
                                        chunk,
                                        Counted,
@@ -973,42 +1086,111 @@ class table_engine {
       kernel<<<grid, route_block_size, smem, stream.get()>>>(
         in, n, stencil, pred, segments, counts, regions, segment_capacity, counter, engine, action);
     }
-    {
-      auto run = [&](auto kpt, auto cas_first) {
-        constexpr int KPT       = decltype(kpt)::value;
-        constexpr bool CasFirst = decltype(cas_first)::value;
-        auto const kernel =
-          blocked_mutate_kernel<block_size, KPT, chunk, CasFirst, Counted, size_type, EngineT, Action>;
-        auto const tiles_per_segment = static_cast<unsigned>(
-          cuco::detail::int_div_ceil(index_type{segment_capacity}, index_type{block_size} * KPT));
-        auto const region_slots = (capacity + num_regions - 1) / num_regions;
-        auto const region_bytes = region_slots * sizeof(value_type);
-        auto const share        = (region_bytes + tiles_per_segment - 1) / tiles_per_segment;
-        blocked_layout const layout{
-          counts,
-          segment_capacity,
-          region_slots,
-          table_bytes,
-          t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
-          1u};
-        kernel<<<dim3{tiles_per_segment, num_regions}, block_size, 0, stream.get()>>>(
-          segments, layout, counter, engine, action);
-      };
-#if defined(CUCO_B200_TUNABLE)
-      auto with_kpt = [&](auto cas_first) {
-        switch (t.blocked_keys_per_thread) {
-          case 1: run(std::integral_constant<int, 1>{}, cas_first); break;
-          case 4: run(std::integral_constant<int, 4>{}, cas_first); break;
-          default: run(std::integral_constant<int, 2>{}, cas_first); break;
-        }
-      };
-      t.blocked_cas_first ? with_kpt(std::true_type{}) : with_kpt(std::false_type{});
-#else
-      run(std::integral_constant<int, 4>{}, std::true_type{});
-#endif
-    }
+    // ---- pass 2 ----
+    this->probe_segments<Counted>(
+      segments, counts, num_regions, 1u, segment_capacity, counter, engine, action, stream);
     this->scratch_free(base, stream.get());
     return true;
+  }
+
+  /// Pass 2 of the blocked path (also the owner side of an exchanged batch, `sources` = ranks):
+  /// probes the staged segments region by region with the region's slots resident in L2.
+  template <bool Counted, typename EngineT, typename Action>
+  void probe_segments(value_type const* segments,
+                      unsigned int const* counts,
+                      std::uint32_t num_regions,
+                      std::uint32_t sources,
+                      std::uint32_t segment_capacity,
+                      size_type* counter,
+                      EngineT const& engine,
+                      Action action,
+                      cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    auto const& t           = tuning();
+    auto const capacity     = static_cast<std::uint64_t>(storage_.capacity());
+    auto const table_bytes  = capacity * sizeof(value_type);
+    auto const region_slots = (capacity + num_regions - 1) / num_regions;
+    constexpr int chunk     = EngineT::sector_chunk_slots;
+
+    if (t.blocked_stream_probe && segment_capacity % 16 == 0 &&
+        (reinterpret_cast<std::uintptr_t>(segments) % 16) == 0) {
+      auto run = [&](auto rows_tag, auto blocks_tag) {
+        constexpr int Rows      = decltype(rows_tag)::value;
+        constexpr int MinBlocks = decltype(blocks_tag)::value;
+        auto const kernel =
+          stream_mutate_kernel<block_size, Rows, chunk, MinBlocks, Counted, size_type, EngineT, Action>;
+        constexpr std::size_t smem = stream_mutate_smem_bytes<block_size, value_type>();
+        if (!opt_in_dynamic_smem(kernel, smem)) { return false; }
+        stream_layout const layout{
+          counts,
+          segment_capacity,
+          static_cast<std::uint32_t>((segment_capacity + stream_chunk_keys - 1) / stream_chunk_keys),
+          num_regions * sources,
+          sources,
+          region_slots,
+          table_bytes,
+          (t.blocked_prefetch ? 1u : 0u) | (t.stream_scout ? 2u : 0u)};
+        static int const resident = [&] {
+          int per_sm = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_size, smem);
+          return std::max(1, per_sm) * cuco::detail::multiprocessor_count();
+        }();
+        auto const items = static_cast<std::uint64_t>(layout.num_segments) * layout.chunks_per_segment;
+        auto const ctas  = (items + block_size / 32 - 1) / (block_size / 32);
+        auto const grid  = static_cast<unsigned>(std::max<std::uint64_t>(1, std::min<std::uint64_t>(ctas, resident)));
+        // the ticket counter that hands the chunks out in region order
+        auto* ticket = static_cast<unsigned long long*>(this->scratch_alloc(sizeof(unsigned long long), stream.get()));
+        if (ticket == nullptr) { return false; }
+        cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream.get());
+        kernel<<<grid, block_size, smem, stream.get()>>>(segments, layout, ticket, counter, engine, action);
+        this->scratch_free(ticket, stream.get());
+        return true;
+      };
+      bool launched = false;
+#if defined(CUCO_B200_TUNABLE)
+      switch (t.stream_slots) {
+        case 1: launched = run(std::integral_constant<int, 1>{}, std::integral_constant<int, 6>{}); break;
+        default: launched = run(std::integral_constant<int, 2>{}, std::integral_constant<int, 4>{}); break;
+      }
+#else
+      launched = run(std::integral_constant<int, 2>{}, std::integral_constant<int, 4>{});
+#endif
+      if (launched) { return; }
+    }
+
+    auto run = [&](auto kpt, auto cas_first) {
+      constexpr int KPT       = decltype(kpt)::value;
+      constexpr bool CasFirst = decltype(cas_first)::value;
+      auto const kernel =
+        blocked_mutate_kernel<block_size, KPT, chunk, CasFirst, Counted, size_type, EngineT, Action>;
+      auto const tiles_per_segment = static_cast<unsigned>(
+        cuco::detail::int_div_ceil(index_type{segment_capacity}, index_type{block_size} * KPT));
+      auto const region_bytes = region_slots * sizeof(value_type);
+      auto const shares       = static_cast<std::uint64_t>(tiles_per_segment) * sources;
+      auto const share        = (region_bytes + shares - 1) / shares;
+      blocked_layout const layout{
+        counts,
+        segment_capacity,
+        region_slots,
+        table_bytes,
+        t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
+        sources};
+      kernel<<<dim3{tiles_per_segment, num_regions * sources}, block_size, 0, stream.get()>>>(
+        segments, layout, counter, engine, action);
+    };
+#if defined(CUCO_B200_TUNABLE)
+    auto with_kpt = [&](auto cas_first) {
+      switch (t.blocked_keys_per_thread) {
+        case 1: run(std::integral_constant<int, 1>{}, cas_first); break;
+        case 4: run(std::integral_constant<int, 4>{}, cas_first); break;
+        default: run(std::integral_constant<int, 2>{}, cas_first); break;
+      }
+    };
+    t.blocked_cas_first ? with_kpt(std::true_type{}) : with_kpt(std::false_type{});
+#else
+    run(std::integral_constant<int, 4>{}, std::true_type{});
+#endif
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1037,7 +1219,7 @@ class table_engine {
     auto const segments = regions * static_cast<std::uint64_t>(num_ranks);
     auto const mean     = (static_cast<std::uint64_t>(n_max) + segments - 1) / segments;
     return exchange_plan{static_cast<std::uint32_t>(regions),
-                         static_cast<std::uint32_t>(mean + mean / 16 + 1024),
+                         static_cast<std::uint32_t>((mean + mean / 16 + 1024 + 15) / 16 * 16),
                          static_cast<std::uint32_t>(
                            std::max<std::uint64_t>(65536, static_cast<std::uint64_t>(n_max) / 8))};
   }
@@ -1121,8 +1303,6 @@ class table_engine {
       CUCO_FAIL("the exchange path needs slots that one CAS can claim (4, 8 or packed 16 bytes)");
     } else {
     CUCO_EXPECTS(this->fast_path_ok(true), "the exchange path needs container-owned storage without tombstones");
-    auto const& t           = tuning();
-    auto const capacity     = static_cast<std::uint64_t>(storage_.capacity());
     if (plan.num_regions == 1 && num_ranks > 1) {
       // owner-only routing: the received segments are an ordinary (gappy) batch; the bulk path
       // regroups it by L2 region locally when that pays
@@ -1137,25 +1317,15 @@ class table_engine {
                                    stream);
       return;
     }
-    constexpr int chunk     = engine_t::sector_chunk_slots;
-    constexpr int kpt       = 4;
-    auto const kernel       = blocked_mutate_kernel<block_size, kpt, chunk, true, false, size_type, engine_t, Action>;
-    auto const tiles_per_segment = static_cast<unsigned>(
-      cuco::detail::int_div_ceil(index_type{plan.segment_capacity}, index_type{block_size} * kpt));
-    auto const region_slots = (capacity + plan.num_regions - 1) / plan.num_regions;
-    auto const region_bytes = region_slots * sizeof(value_type);
-    auto const shares       = static_cast<std::uint64_t>(tiles_per_segment) * num_ranks;
-    auto const share        = (region_bytes + shares - 1) / shares;
-    blocked_layout const layout{counts_recv,
-                                plan.segment_capacity,
-                                region_slots,
-                                capacity * sizeof(value_type),
-                                t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
-                                static_cast<std::uint32_t>(num_ranks)};
-    kernel<<<dim3{tiles_per_segment, plan.num_regions * static_cast<unsigned>(num_ranks)},
-             block_size,
-             0,
-             stream.get()>>>(segments, layout, static_cast<size_type*>(nullptr), engine, action);
+    this->template probe_segments<false>(segments,
+                                         counts_recv,
+                                         plan.num_regions,
+                                         static_cast<std::uint32_t>(num_ranks),
+                                         plan.segment_capacity,
+                                         static_cast<size_type*>(nullptr),
+                                         engine,
+                                         action,
+                                         stream);
     }
   }
 

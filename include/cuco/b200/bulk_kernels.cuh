@@ -346,7 +346,7 @@ __device__ bool mutate_slow_path(
   using slot_type    = typename Engine::value_type;
   auto const desired = engine.native_value(val);
   auto const res     = engine.template insert_driver<ChunkSlots, Policy>(
-    val, [&](slot_type* t, slot_type& e, auto const&) { return engine.try_claim(t, e, desired); });
+    val, [&](slot_type* t, slot_type& e, auto const& v) { return engine.try_claim(t, e, desired, Engine::key_of(v)); });
   if (res.second) {
     action.on_new(engine, idx, res.first, desired);
   } else {
@@ -562,14 +562,14 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void generic_mutate_kernel(InputIt firs
     constexpr bool key_only_claim = Action::key_then_apply && sizeof(slot_type) > 8;
 
     auto const res = engine.template insert_driver<Engine::window_chunk_slots, load_policy::plain>(
-      val, [&](slot_type* target, slot_type& expected, auto const&) {
+      val, [&](slot_type* target, slot_type& expected, auto const& v) {
         if constexpr (key_only_claim) {
           key_type expected_key = Engine::key_of(expected);
-          auto const r          = engine.try_claim_key(target, expected_key, desired.first);
-          expected.first        = expected_key;
+          auto const r = engine.try_claim_key(target, expected_key, desired.first, Engine::key_of(v));
+          expected.first = expected_key;
           return r;
         } else {
-          return engine.try_claim(target, expected, desired);
+          return engine.try_claim(target, expected, desired, Engine::key_of(v));
         }
       });
     if (res.second) {
@@ -686,7 +686,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void route_kernel(InputIt first,
   constexpr index_type tile    = index_type{BlockSize} * items;
   constexpr int regions_per_thread = (route_max_regions + BlockSize - 1) / BlockSize;
 
-  extern __shared__ __align__(16) unsigned char route_dynamic_smem[];
+  extern __shared__ __align__(128) unsigned char route_dynamic_smem[];
   auto* const stage = reinterpret_cast<slot_type*>(route_dynamic_smem);            // [tile]
   auto* const owner = reinterpret_cast<std::uint16_t*>(stage + tile);              // [tile]
   __shared__ unsigned int tile_hist[route_max_regions];    // elements of this tile per region
@@ -1152,7 +1152,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize, 2) void exchange_route_kernel(
   constexpr index_type tile = index_type{BlockSize} * items;
   constexpr int buckets_per_thread = (route_max_regions + BlockSize - 1) / BlockSize;
 
-  extern __shared__ __align__(16) unsigned char route_dynamic_smem[];
+  extern __shared__ __align__(128) unsigned char route_dynamic_smem[];
   auto* const stage  = reinterpret_cast<elem_type*>(route_dynamic_smem);   // [tile]
   auto* const origin = reinterpret_cast<std::uint32_t*>(stage + tile);     // [tile] (KeysOnly)
   auto* const bucket_of =

@@ -19,10 +19,14 @@
 //    policy; slot claims are single 32/64/128-bit CAS when the slot allows it (slot_ops.cuh) and
 //    fall back to key-CAS + payload store otherwise.
 //
-//  * Tombstone-aware insertion: an erased slot is remembered as candidate while the scan continues
-//    to the first truly empty slot, so re-inserting after erase cannot duplicate a key (the
-//    reference takes the first available slot, ref_impl.cuh:385-409). Without tombstones the two
-//    rules coincide.
+//  * Insertion takes the FIRST AVAILABLE slot (empty or erased) of the probe sequence, the
+//    reference's rule (ref_impl.cuh:385-409): re-inserting a key that still sits further down its
+//    cluster after a neighbour was erased stores it a second time, exactly as cuco does
+//    (tests/test_baseline_configs_gpu.py::test_insert_after_erase_follows_cuco pins size(), the insert
+//    count and lookups against cuco's own build). Compile with -DCUCO_B200_TOMBSTONE_AWARE_INSERT=1
+//    for the stricter opt-in rule: an erased slot is only remembered as candidate while the scan
+//    continues to the first truly empty slot (at most one full cycle), so a key can never be stored
+//    twice. Without tombstones the two rules coincide.
 //
 // Result semantics (what parity is defined over) are those of SURVEY.md §8(a').
 #pragma once
@@ -145,6 +149,13 @@ class probe_engine {
     (slot_bytes & (slot_bytes - 1)) == 0 && alignof(value_type) >= sizeof(value_type);
   /// Slots claimable with one hardware CAS (32/64/128 bit).
   static constexpr bool single_cas = is_single_cas_slot<value_type>();
+  /// Insert rule on tables with an erased-key sentinel: false = the reference's first-AVAILABLE rule
+  /// (default, bit-exact with cuco), true = opt-in stricter rule (see the header comment).
+#if defined(CUCO_B200_TOMBSTONE_AWARE_INSERT) && CUCO_B200_TOMBSTONE_AWARE_INSERT
+  static constexpr bool tombstone_aware_insert = true;
+#else
+  static constexpr bool tombstone_aware_insert = false;
+#endif
 
   /// Chunk (in slots) that is always safe to load: one window, or one slot for odd geometries.
   static constexpr int window_chunk_slots =
@@ -552,6 +563,18 @@ class probe_engine {
                                                    value_type& expected,
                                                    value_type const& desired) const noexcept
   {
+    return this->try_claim(address, expected, desired, key_of(desired));
+  }
+
+  /// Same, for a key that arrived in its own (heterogeneous) type: the duplicate test applies the
+  /// user's predicate to THAT key, as the reference does (ref_impl.cuh:385-409), never to the
+  /// converted one.
+  template <typename ProbeKey>
+  [[nodiscard]] __device__ insert_result try_claim(value_type* address,
+                                                   value_type& expected,
+                                                   value_type const& desired,
+                                                   ProbeKey const& probe_key) const noexcept
+  {
     if constexpr (single_cas) {
       auto const observed = cas_slot<Scope>(address, expected, desired);
       if (same_bits(observed, expected)) { return insert_result::SUCCESS; }
@@ -571,7 +594,7 @@ class probe_engine {
     }
     if constexpr (!allows_duplicates) {
       if (!same_bits(key_of(expected), key_of(empty_slot_)) && !same_bits(key_of(expected), erased_key_) &&
-          eq_(key_of(desired), key_of(expected))) {
+          eq_(probe_key, key_of(expected))) {
         return insert_result::DUPLICATE;
       }
     }
@@ -604,7 +627,8 @@ class probe_engine {
     auto const& key      = key_of(val);
     auto const start     = make_cursor(key);
     auto* const table    = slots();
-    bool const tombstone = has_tombstones();
+    bool const tombstone = tombstone_aware_insert && has_tombstones();
+    size_type seen       = 0;  // slots visited (strict rule only): bounds the walk to one full cycle
 
     while (true) {  // restarted only after losing a tombstone candidate to another key
       value_type* found   = nullptr;
@@ -615,6 +639,7 @@ class probe_engine {
 
       walk<ChunkSlots, Policy>(start, [&](size_type index, value_type slot) {
         auto const state = classify_insert(key, key_of(slot));
+        if (tombstone) { ++seen; }
         if constexpr (!allows_duplicates) {
           if (state == equal_result::EQUAL) {
             found = table + index;
@@ -623,7 +648,10 @@ class probe_engine {
         }
         if (state != equal_result::AVAILABLE) { return false; }
 
-        bool const truly_empty = !tombstone || is_empty_key(key_of(slot));
+        bool truly_empty = !tombstone || is_empty_key(key_of(slot));
+        if (tombstone && !truly_empty && cand != nullptr && seen > static_cast<size_type>(capacity())) {
+          truly_empty = true;  // one full cycle without an empty slot: settle for the remembered tombstone
+        }
         if (!truly_empty) {
           // tombstone: remember the first one, keep looking for the key further down the cluster
           if (cand == nullptr) {
@@ -672,7 +700,7 @@ class probe_engine {
     auto const val = this->heterogeneous_value(value);
     auto const res = insert_driver<ChunkSlots, Policy>(
       val, [&](value_type* target, value_type& expected, auto const& v) {
-        return try_claim(target, expected, native_value(v));
+        return try_claim(target, expected, native_value(v), key_of(v));
       });
     return res.second;
   }
@@ -685,7 +713,7 @@ class probe_engine {
     auto const val = this->heterogeneous_value(value);
     auto const res = insert_driver<ChunkSlots, Policy>(
       val, [&](value_type* target, value_type& expected, auto const& v) {
-        return try_claim(target, expected, native_value(v));
+        return try_claim(target, expected, native_value(v), key_of(v));
       });
     if constexpr (has_payload) {
       // a two-step writer (padded slots, insert_or_assign/apply) may not have published yet
@@ -886,7 +914,7 @@ class probe_engine {
   {
     auto const val = this->heterogeneous_value(value);
     return tile_insert_driver(tile, val, [&](value_type* t, value_type& e, auto const& v) {
-             return try_claim(t, e, native_value(v));
+             return try_claim(t, e, native_value(v), key_of(v));
            }).second;
   }
 
@@ -896,7 +924,7 @@ class probe_engine {
   {
     auto const val = this->heterogeneous_value(value);
     auto const res = tile_insert_driver(tile, val, [&](value_type* t, value_type& e, auto const& v) {
-      return try_claim(t, e, native_value(v));
+      return try_claim(t, e, native_value(v), key_of(v));
     });
     if constexpr (has_payload) {
       if (!res.second || !single_cas) {
@@ -1030,13 +1058,22 @@ class probe_engine {
                                                        key_type& expected_key,
                                                        key_type const& desired_key) const noexcept
   {
+    return this->try_claim_key(address, expected_key, desired_key, desired_key);
+  }
+
+  template <typename ProbeKey>
+  [[nodiscard]] __device__ insert_result try_claim_key(value_type* address,
+                                                       key_type& expected_key,
+                                                       key_type const& desired_key,
+                                                       ProbeKey const& probe_key) const noexcept
+  {
     static_assert(has_payload);
     cuda::atomic_ref<key_type, Scope> key_ref{address->first};
     if (key_ref.compare_exchange_strong(expected_key, desired_key, cuda::memory_order_relaxed)) {
       return insert_result::SUCCESS;
     }
     if (!same_bits(expected_key, key_of(empty_slot_)) && !same_bits(expected_key, erased_key_) &&
-        eq_(desired_key, expected_key)) {
+        eq_(probe_key, expected_key)) {
       return insert_result::DUPLICATE;
     }
     return insert_result::CONTINUE;

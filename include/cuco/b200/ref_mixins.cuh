@@ -242,7 +242,7 @@ struct mixin_insert_or_assign : mixin_base<Ref, op::insert_or_assign_tag> {
     auto const val   = e.heterogeneous_value(value);
     auto const image = e.native_value(val);
     auto const res   = e.template insert_driver<engine_t::window_chunk_slots, load_policy::plain>(
-      val, [&](slot_t* t, slot_t& expected, auto const&) { return e.try_claim(t, expected, image); });
+      val, [&](slot_t* t, slot_t& expected, auto const& v) { return e.try_claim(t, expected, image, engine_t::key_of(v)); });
     if (!res.second) { store_payload<engine_t>(res.first, image); }
   }
 
@@ -256,7 +256,7 @@ struct mixin_insert_or_assign : mixin_base<Ref, op::insert_or_assign_tag> {
     auto const val   = e.heterogeneous_value(value);
     auto const image = e.native_value(val);
     auto const res   = e.tile_insert_driver(
-      group, val, [&](slot_t* t, slot_t& expected, auto const&) { return e.try_claim(t, expected, image); });
+      group, val, [&](slot_t* t, slot_t& expected, auto const& v) { return e.try_claim(t, expected, image, engine_t::key_of(v)); });
     if (!res.second && group.thread_rank() == 0) { store_payload<engine_t>(res.first, image); }
   }
 
@@ -332,16 +332,17 @@ struct mixin_insert_or_apply : mixin_base<Ref, op::insert_or_apply_tag> {
   }
 
   /// Claim used by both flavours. Direct mode on 16-byte slots claims the key half only.
-  template <bool Direct, typename Engine, typename Slot>
-  __device__ static auto claim(Engine& e, Slot* target, Slot& expected, Slot const& image)
+  template <bool Direct, typename Engine, typename Slot, typename ProbeKey>
+  __device__ static auto claim(
+    Engine& e, Slot* target, Slot& expected, Slot const& image, ProbeKey const& probe_key)
   {
     if constexpr (Direct && sizeof(Slot) > 8) {
       auto expected_key = expected.first;
-      auto const r      = e.try_claim_key(target, expected_key, image.first);
+      auto const r      = e.try_claim_key(target, expected_key, image.first, probe_key);
       expected.first    = expected_key;
       return r;
     } else {
-      return e.try_claim(target, expected, image);
+      return e.try_claim(target, expected, image, probe_key);
     }
   }
 
@@ -371,8 +372,8 @@ struct mixin_insert_or_apply : mixin_base<Ref, op::insert_or_apply_tag> {
     auto const val   = e.heterogeneous_value(value);
     auto const image = e.native_value(val);
     auto const res   = e.template insert_driver<engine_t::window_chunk_slots, load_policy::plain>(
-      val, [&](slot_t* t, slot_t& expected, auto const&) {
-        return claim<Direct>(e, t, expected, image);
+      val, [&](slot_t* t, slot_t& expected, auto const& v) {
+        return claim<Direct>(e, t, expected, image, engine_t::key_of(v));
       });
     settle<Direct>(e, res.first, image, res.second, op);
     return res.second;
@@ -387,8 +388,8 @@ struct mixin_insert_or_apply : mixin_base<Ref, op::insert_or_apply_tag> {
     auto const val   = e.heterogeneous_value(value);
     auto const image = e.native_value(val);
     auto const res   = e.tile_insert_driver(
-      group, val, [&](slot_t* t, slot_t& expected, auto const&) {
-        return claim<Direct>(e, t, expected, image);
+      group, val, [&](slot_t* t, slot_t& expected, auto const& v) {
+        return claim<Direct>(e, t, expected, image, engine_t::key_of(v));
       });
     if (group.thread_rank() == 0) { settle<Direct>(e, res.first, image, res.second, op); }
     return res.second;

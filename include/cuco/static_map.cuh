@@ -18,6 +18,7 @@
 #include <cuco/b200/bulk_engine.cuh>
 #include <cuco/b200/table_scan.cuh>
 #include <cuco/detail/__config>
+#include <cuco/detail/static_map/kernels.cuh>
 #include <cuco/extent.cuh>
 #include <cuco/hash_functions.cuh>
 #include <cuco/pair.cuh>

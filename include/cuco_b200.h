@@ -49,7 +49,9 @@ enum cuco_b200_kind {
   CUCO_B200_MULTISET_I64_LP1_W2 = 11, /* static_multiset<int64>     linear_probing<1> w2 */
   CUCO_B200_MULTIMAP_I64_LP4    = 12, /* experimental::static_multimap<int64,int64> linear_probing<4> w1 (class default):
                                          insert, insert_if, contains, contains_if, count only */
-  CUCO_B200_NUM_KINDS         = 13
+  CUCO_B200_MAP_I64_LP1_X64     = 13, /* static_map<int64,int64>      linear_probing<1, xxhash_64> w1: the hash-partitioned
+                                         benchmark table; a 32-bit hash folds unevenly onto shards of 1 - 4 G slots */
+  CUCO_B200_NUM_KINDS         = 14
 };
 
 /* Reduction selector for cuco_b200_insert_or_apply (cuco::reduce::plus / min / max,
@@ -217,6 +219,12 @@ int cuco_b200_set_blocking(int mode, int region_mib);
 /* Pass 2 of the blocked path: probes in flight per thread (1, 2, 4), whether a probe starts with the
  * CAS, whether the next region is prefetched into L2. Negative / other = leave unchanged. */
 int cuco_b200_set_blocking_variant(int keys_per_thread, int cas_first, int prefetch);
+/* Kernels of the blocked path: tile_route != 0 -> pass 1 is the persistent router fed by the bulk-copy
+ * engine (contiguous, 16-byte aligned batches of slot images; anything else keeps the round-1
+ * router); stream_probe != 0 -> pass 2 is the warp-persistent refilling probe stream (else the
+ * round-1 one-tile-per-CTA kernel); slots in {2,3,4} = probes in flight per lane of that stream
+ * (instantiations with run-time tuning only). Negative / other = leave unchanged. */
+int cuco_b200_set_stream_variant(int tile_route, int stream_probe, int slots);
 
 /* ---- hash-partitioned multi-GPU support (no reference counterpart) --------------
  * owner(key) = mulhi64(murmur_fmix64(key ^ salt), num_parts): high bits of a mix that is independent

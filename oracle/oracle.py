@@ -125,6 +125,7 @@ KIND_GEOMETRY = {
     10: (4, 0, 4, 2, DOUBLE, XXHASH32),
     11: (8, 0, 1, 2, LINEAR, XXHASH32),
     12: (8, 8, 4, 1, LINEAR, XXHASH32),
+    13: (8, 8, 1, 1, LINEAR, XXHASH64),
 }
 MULTI_KINDS = {10, 11, 12}  # static_multiset / multimap instantiations: equal keys are stored repeatedly
 

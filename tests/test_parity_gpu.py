@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 MAP_KINDS = [_cabi.MAP_I64_LP1, _cabi.MAP_I64_DH8, _cabi.MAP_I32_LP4, _cabi.MAP_I64_LP4,
              _cabi.MAP_I64_LP1_W2, _cabi.MAP_I32_DH2_W2_MM, _cabi.MAP_I32I64_LP1,
-             _cabi.MAP_I64_DH8_X64]
+             _cabi.MAP_I64_DH8_X64, _cabi.MAP_I64_LP1_X64]
 SET_KINDS = [_cabi.SET_I32_DH4, _cabi.SET_I64_DH4]
 TUNINGS = [  # (keys_per_thread, cas_first, sector_chunks, force_generic, coherent_loads, waves)
     (12, 0, 1, 0, 0, 0), (1, 0, 0, 0, 1, 1), (4, 1, 1, 0, 0, 2), (4, 0, 1, 0, 1, 0), (2, 1, 1, 1, 0, 0),
@@ -293,8 +293,13 @@ def test_full_size_round_trip_properties(native_lib):
     torch.cuda.empty_cache()
 
 
-BLOCKED_VARIANTS = [  # (region MiB or -KiB, keys per thread, cas_first, prefetch)
-    (1, 2, 0, 1), (-16, 1, 1, 1), (-64, 4, 1, 0), (-16, 4, 0, 1), (-256, 2, 1, 1)]
+BLOCKED_VARIANTS = [
+    # (region MiB or -KiB, keys per thread, cas_first, prefetch, tile_route, stream_probe, slots)
+    (1, 2, 0, 1, 0, 0, 2), (-16, 1, 1, 1, 0, 0, 2), (-64, 4, 1, 0, 0, 0, 2), (-16, 4, 0, 1, 0, 0, 2),
+    (-256, 2, 1, 1, 0, 0, 2),
+    # round-2 kernels: bulk-copy fed router and warp-persistent probe stream, alone and together
+    (-16, 4, 1, 1, 1, 0, 2), (-16, 4, 1, 1, 0, 1, 2), (-64, 4, 1, 1, 1, 1, 2), (-16, 4, 1, 0, 1, 1, 1),
+    (1, 4, 1, 1, 1, 1, 1), (-256, 4, 1, 1, 1, 1, 2)]
 
 
 @pytest.mark.parametrize("variant", BLOCKED_VARIANTS)
@@ -308,6 +313,8 @@ def test_l2_blocked_mutations_match_oracle(kind, variant, native_lib):
     try:
         native_lib.set_blocking(1, variant[0])  # always on
         native_lib.set_blocking_variant(variant[1], variant[2], variant[3])
+        native_lib.set_stream_variant(variant[4], variant[5], variant[6])
+        aos = bool(variant[4]) and is_map  # the bulk-copy router takes arrays of slot images (AoS pairs)
         streams = {
             "uniform": keyset(kind, n, 21, hi=n),
             "skewed": np.concatenate([np.full(n - 100, 7, dtype=np.int64), np.arange(100, dtype=np.int64) + 100]),
@@ -319,23 +326,31 @@ def test_l2_blocked_mutations_match_oracle(kind, variant, native_lib):
             ref = oracle.Table.for_kind(kind, n, 0.5)
             dk = dev(keys, k.key)
             dv = dev(vals, k.value) if is_map else None
-            assert t.insert(dk, dv) == ref.insert(keys, vals if is_map else None), name
+
+            def batch(values):
+                # (keys, values) arguments of a bulk call: one [n, 2] array of pairs, or two arrays
+                if aos:
+                    return (torch.stack([dk, dev(values, k.value)], dim=1).contiguous(), None)
+                return (dk, dev(values, k.value) if is_map else None)
+
+            assert t.insert(*batch(vals)) == ref.insert(keys, vals if is_map else None), name
             assert t.size() == ref.size(), name
             q = np.concatenate([keys[::3], keyset(kind, 1000, 22, hi=8 * n)])
             assert np.array_equal(t.find(dev(q, k.key)).cpu().numpy(), ref.find(q)), name
-            assert t.insert(dk, dv) == 0, name  # second pass through the blocked path: all present
+            assert t.insert(*batch(vals)) == 0, name  # second pass through the blocked path: all present
             if is_map:
-                t.insert_or_assign(dk, dev(vals + 9, k.value)); ref.insert_or_assign(keys, vals + 9)
+                t.insert_or_assign(*batch(vals + 9)); ref.insert_or_assign(keys, vals + 9)
                 assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
                 t.clear(); ref.clear()
                 ones = np.ones(n, dtype=np.int64)
-                t.insert_or_apply(dk, dev(ones, k.value), op="plus"); ref.insert_or_apply(keys, ones, oracle.PLUS)
+                t.insert_or_apply(*batch(ones), op="plus"); ref.insert_or_apply(keys, ones, oracle.PLUS)
                 assert t.size() == ref.size()
                 assert np.array_equal(t.find(dk).cpu().numpy(), ref.find(keys)), name
             t.close()
     finally:
         native_lib.set_blocking(-1, 16)
         native_lib.set_blocking_variant(4, 1, 1)
+        native_lib.set_stream_variant(1, 0, 2)  # the defaults of tuning_t
 
 
 def test_l2_blocked_large_batch_properties(native_lib):
