@@ -237,9 +237,10 @@ def run_single(args, lib, impl):
             traffic = {}
     if impl == "native":
         find_traffic = traffic.get("lookup_kernel")
-        ins_traffic = (traffic.get("route_kernel", 0) + traffic.get("blocked_mutate_kernel", 0)) if blocked else None
+        router = "tile_route_kernel" if "tile_route_kernel" in traffic else "route_kernel"
+        ins_traffic = (traffic.get(router, 0) + traffic.get("blocked_mutate_kernel", 0)) if blocked else None
         find_kernel = "find: lookup_kernel (one launch = the whole find pass)"
-        ins_kernel = ("insert: route_kernel + blocked_mutate_kernel (two launches)" if blocked
+        ins_kernel = (f"insert: {router} + blocked_mutate_kernel (two launches)" if blocked
                       else "insert: mutate_kernel")
     else:
         find_traffic, ins_traffic = traffic.get("find"), traffic.get("insert_if_n")
@@ -294,7 +295,59 @@ def run_single(args, lib, impl):
     # timed step of the headline configuration
     if not args.no_points:
         result["c2_points"] = run_points(args, lib, dev, keys, pairs, out)
+        result["sweep"] = run_sweep(lib, dev, keys, pairs, out)
     return result
+
+
+def run_sweep(lib, dev, keys, pairs, out, reps=5):
+    """The reference benchmarks' sweep axes (benchmarks/benchmark_defaults.hpp:28-52) on the headline
+    instantiation (static_map<int64,int64>, linear_probing<1>), one axis at a time around the defaults:
+    occupancy 0.1 - 0.9 (insert_bench.cu, find_bench.cu), matching rate of the find queries 0 / 0.5
+    (find_bench.cu:57-59: dropout), key multiplicity 8 and Gaussian skew 0.5 (key_generator.cuh).
+    Median of `reps` after 2 warm-ups, Gops/s; every find output is checked."""
+    import cucollections_b200 as cb
+    from cucollections_b200 import key_generator as kg
+    stream = torch.cuda.current_stream(dev)
+    n = keys.numel()
+
+    def measure(label, lf, k, p, q, expect):
+        t = cb.static_map(n=n, load_factor=lf, probing="linear_probing", cg_size=1, device=dev, _library=lib)
+        ins, fnd = [], []
+        for i in range(2 + reps):
+            t.clear_async()
+            ei = timed(lambda: t.insert_async(p), stream)
+            ef = timed(lambda: t.find(q, out), stream)
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                ins.append(ei[0].elapsed_time(ei[1]))
+                fnd.append(ef[0].elapsed_time(ef[1]))
+        ok = bool((out == expect).all().item())
+        t.close()
+        del t
+        torch.cuda.empty_cache()
+        return {**label, "load_factor": lf, "insert_gops": n / (statistics.median(ins) * 1e-3) / 1e9,
+                "find_gops": n / (statistics.median(fnd) * 1e-3) / 1e9, "find_output_checked": ok}
+
+    rows = []
+    for lf in (0.1, 0.3, 0.7, 0.9):
+        rows.append(measure({"axis": "occupancy"}, lf, keys, pairs, keys, keys))
+    for rate in (0.0, 0.5):
+        q = kg.dropout(keys, rate, seed=43) if rate > 0 else keys + (n + 1)  # uniform keys live in [1, n]
+        q = torch.where(q == n, q + 1, q)  # n itself may or may not have been drawn: keep the expectation exact
+        present = q < n
+        expect = torch.where(present, q, torch.full_like(q, -1))
+        rows.append(measure({"axis": "matching_rate", "matching_rate": rate}, 0.5, keys, pairs, q, expect))
+        del q, present, expect
+    k8 = kg.uniform(n, 8, torch.int64, dev, seed=42)
+    rows.append(measure({"axis": "multiplicity", "multiplicity": 8}, 0.5, k8, torch.stack([k8, k8], dim=1).contiguous(),
+                        k8, k8))
+    del k8
+    kgauss = kg.gaussian(n, 0.5, torch.int64, dev, seed=42)
+    rows.append(measure({"axis": "skew", "distribution": "gaussian(0.5)"}, 0.5, kgauss,
+                        torch.stack([kgauss, kgauss], dim=1).contiguous(), kgauss, kgauss))
+    del kgauss
+    torch.cuda.empty_cache()
+    return rows
 
 
 def launch_share(op: str, launch: str) -> float:
@@ -429,6 +482,10 @@ def main():
                     help="N > 1: pairs over all GPUs (default: BASELINE configs[3], 4 B)")
     ap.add_argument("--batch", type=int, default=0, help="N > 1: pairs per rank and bulk call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true",
+                    help="N > 1: skip the BASELINE configs[4] leg (insert_or_apply sum, 2 B rows / 10 M keys)")
+    ap.add_argument("--c5-rows", type=int, default=0, help="N > 1: rows of the C5 leg (default 2 B)")
+    ap.add_argument("--c5-distinct", type=int, default=0, help="N > 1: distinct keys of the C5 leg (default 10 M)")
     ap.add_argument("--no-c4", action="store_true",
                     help="N > 1: skip the BASELINE configs[3] leg at its stated size (4 B pairs)")
     args = ap.parse_args()

@@ -74,6 +74,15 @@ _PROTOTYPES = {
     "cuco_b200_exchange_mutate": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _int, _vp]),
     "cuco_b200_exchange_lookup": (_int, [_vp, _vp, _vp, _pvp, _u32, _u32, _int, _int, _int, _vp]),
     "cuco_b200_exchange_unpermute": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp]),
+    "cuco_b200_exchange_stage_plan": (_int, [_vp, _i64, _int, _int, _pu32, _pu32]),
+    "cuco_b200_exchange_stage": (_int, [_vp, _vp, _vp, _i64, _int, _int, _u32, _u32, _int, _int, _u64,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cuco_b200_exchange_publish": (_int, [_vp, _vp, _pvp, _pvp, _int, _u32, _int, _int, _int, _vp]),
+    "cuco_b200_exchange_fine_regions": (_int, [_vp, _int, _pu32]),
+    "cuco_b200_exchange_probe": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _u32, _u32, _int, _vp]),
+    "cuco_b200_copy_async": (_int, [_vp, _vp, _i64, _vp]),
+    "cuco_b200_exchange_apply": (_int, [_vp, _vp, _vp, _u32, _int, _int, _int, _int, _vp]),
+    "cuco_b200_exchange_lookup_local": (_int, [_vp, _vp, _vp, _vp, _u32, _int, _int, _vp]),
     "cuco_b200_set_tuning": (_int, [_int, _int, _int, _int, _int, _int, _int]),
     "cuco_b200_set_blocking": (_int, [_int, _int]),
     "cuco_b200_set_blocking_variant": (_int, [_int, _int, _int]),

@@ -787,6 +787,167 @@ int cuco_b200_exchange_lookup(cuco_b200_table* t,
   });
 }
 
+int cuco_b200_exchange_stage_plan(cuco_b200_table* t,
+                                  int64_t n_max,
+                                  int num_ranks,
+                                  int slices,
+                                  uint32_t* segment_capacity,
+                                  uint32_t* spill_capacity)
+{
+  return guarded([&] {
+    require(t && segment_capacity && spill_capacity, "NULL argument");
+    auto const shape  = t->stage_plan(n_max, num_ranks, slices);
+    *segment_capacity = shape.segment_capacity;
+    *spill_capacity   = shape.spill_capacity;
+  });
+}
+
+int cuco_b200_exchange_stage(cuco_b200_table* t,
+                             const void* keys,
+                             const void* values,
+                             int64_t n,
+                             int keys_only,
+                             int slices,
+                             uint32_t segment_capacity,
+                             uint32_t spill_capacity,
+                             int num_ranks,
+                             int my_rank,
+                             uint64_t salt,
+                             void* stage,
+                             void* counts_local,
+                             void* position_local,
+                             void* spill,
+                             void* spill_index,
+                             void* spill_count,
+                             void* stream)
+{
+  return guarded([&] {
+    require(t && n >= 0 && (keys || n == 0) && stage && counts_local && spill && spill_count, "bad argument");
+    require(!keys_only || (position_local && spill_index), "lookups need the position buffers");
+    require(my_rank >= 0 && my_rank < num_ranks && slices >= 1, "rank or slice count out of range");
+    t->exchange_stage(keys, values, n, keys_only != 0,
+                      cuco_b200_table::exchange_shape{static_cast<uint32_t>(slices), segment_capacity, spill_capacity},
+                      num_ranks, my_rank, salt, stage, counts_local, position_local, spill, spill_index,
+                      spill_count, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_fine_regions(cuco_b200_table* t, int num_ranks, uint32_t* num_regions)
+{
+  return guarded([&] {
+    require(t && num_regions && num_ranks >= 1, "bad argument");
+    *num_regions = t->exchange_fine_regions(num_ranks);
+  });
+}
+
+int cuco_b200_exchange_probe(cuco_b200_table* t,
+                             const void* segments,
+                             const void* counts_recv,
+                             uint32_t num_regions,
+                             uint32_t segment_capacity,
+                             int num_ranks,
+                             uint32_t region_begin,
+                             uint32_t region_count,
+                             int reduce_op,
+                             void* stream)
+{
+  return guarded([&] {
+    require(t && segments && counts_recv, "NULL argument");
+    t->exchange_probe(segments, counts_recv, num_regions, segment_capacity, num_ranks, region_begin, region_count,
+                      reduce_op, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_publish(const void* counts_local,
+                               const void* spill_count,
+                               void* const* peer_counts,
+                               void* const* peer_flags,
+                               int slices,
+                               uint32_t segment_capacity,
+                               int num_ranks,
+                               int my_rank,
+                               int source_major,
+                               void* stream)
+{
+  return guarded([&] {
+#if defined(CUCO_SHIM_REFERENCE)
+    (void)counts_local, (void)spill_count, (void)peer_counts, (void)peer_flags, (void)slices;
+    (void)segment_capacity, (void)num_ranks, (void)my_rank, (void)stream, (void)source_major;
+    throw std::invalid_argument("the exchange path exists in the native build only");
+#else
+    require(counts_local && spill_count && peer_counts && peer_flags, "NULL argument");
+    require(num_ranks >= 1 && num_ranks <= cuco::b200::exchange_max_ranks && my_rank >= 0 && my_rank < num_ranks &&
+              slices >= 1,
+            "rank or slice count out of range");
+    cuco::b200::exchange_peers counts{}, flags{};
+    for (int r = 0; r < num_ranks; ++r) {
+      counts.base[r] = peer_counts[r];
+      flags.base[r]  = peer_flags[r];
+    }
+    cuco::b200::exchange_geometry const geometry{static_cast<std::uint32_t>(num_ranks),
+                                                 static_cast<std::uint32_t>(my_rank),
+                                                 static_cast<std::uint32_t>(slices),
+                                                 segment_capacity,
+                                                 0,
+                                                 source_major ? 1u : static_cast<std::uint32_t>(num_ranks),
+                                                 source_major ? static_cast<std::uint32_t>(my_rank) * slices
+                                                              : static_cast<std::uint32_t>(my_rank)};
+    auto const buckets = static_cast<unsigned>(num_ranks) * static_cast<unsigned>(slices);
+    cuco::b200::exchange_publish_kernel<<<(buckets + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<unsigned int const*>(counts_local), static_cast<unsigned int const*>(spill_count), counts, flags,
+      geometry);
+    check_launch();
+#endif
+  });
+}
+
+int cuco_b200_copy_async(void* dst, const void* src, int64_t bytes, void* stream)
+{
+  return guarded([&] {
+    require(bytes >= 0 && ((dst && src) || bytes == 0), "bad argument");
+    if (bytes == 0) { return; }
+    auto const status =
+      cudaMemcpyAsync(dst, src, static_cast<std::size_t>(bytes), cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+    if (status != cudaSuccess) { throw std::runtime_error(cudaGetErrorString(status)); }
+  });
+}
+
+int cuco_b200_exchange_apply(cuco_b200_table* t,
+                             const void* segments,
+                             const void* counts_recv,
+                             uint32_t segment_capacity,
+                             int num_ranks,
+                             int slice,
+                             int slices,
+                             int reduce_op,
+                             void* stream)
+{
+  return guarded([&] {
+    require(t && segments && counts_recv, "NULL argument");
+    require(slice >= 0 && slice < slices && num_ranks >= 1, "slice out of range");
+    t->exchange_apply(segments, counts_recv, segment_capacity, num_ranks, slice, slices, reduce_op, stream);
+    check_launch();
+  });
+}
+
+int cuco_b200_exchange_lookup_local(cuco_b200_table* t,
+                                    const void* segments,
+                                    const void* counts_recv,
+                                    void* results,
+                                    uint32_t segment_capacity,
+                                    int num_ranks,
+                                    int what,
+                                    void* stream)
+{
+  return guarded([&] {
+    require(t && segments && counts_recv && results, "NULL argument");
+    t->exchange_lookup_local(segments, counts_recv, results, segment_capacity, num_ranks, what, stream);
+    check_launch();
+  });
+}
+
 int cuco_b200_exchange_unpermute(cuco_b200_table* t,
                                  const void* results,
                                  const void* position_local,

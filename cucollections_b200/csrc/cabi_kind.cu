@@ -367,6 +367,26 @@ class table_impl final : public cuco_b200_table {
     throw unsupported();
   }
   void exchange_unpermute(const void*, const void*, i64, void*, int, void*) override { throw unsupported(); }
+  exchange_shape stage_plan(i64, int, int) override { throw unsupported(); }
+  void exchange_stage(const void*, const void*, i64, bool, exchange_shape, int, int, std::uint64_t, void*, void*,
+                      void*, void*, void*, void*, void*) override
+  {
+    throw unsupported();
+  }
+  void exchange_apply(const void*, const void*, std::uint32_t, int, int, int, int, void*) override
+  {
+    throw unsupported();
+  }
+  void exchange_lookup_local(const void*, const void*, void*, std::uint32_t, int, int, void*) override
+  {
+    throw unsupported();
+  }
+  std::uint32_t exchange_fine_regions(int) override { throw unsupported(); }
+  void exchange_probe(const void*, const void*, std::uint32_t, std::uint32_t, int, std::uint32_t, std::uint32_t, int,
+                      void*) override
+  {
+    throw unsupported();
+  }
   static std::invalid_argument unsupported()
   {
     return std::invalid_argument("the exchange path exists in the native build of maps and sets only");
@@ -451,6 +471,119 @@ class table_impl final : public cuco_b200_table {
       eng.template exchange_lookup_async<std::uint8_t>(segs, cnts, to_peers(peer_results, num_ranks),
                                                        to_plan(shape), num_ranks, my_rank, handle,
                                                        cuco::b200::emit_present{}, sref(s));
+    }
+  }
+
+  exchange_shape stage_plan(i64 n_max, int num_ranks, int groups) override
+  {
+    auto const p = c_.b200_engine().plan_stage(n_max, num_ranks, groups);
+    return exchange_shape{p.num_regions, p.segment_capacity, p.spill_capacity};
+  }
+
+  void exchange_stage(const void* keys, const void* values, i64 n, bool keys_only, exchange_shape shape,
+                      int num_ranks, int my_rank, std::uint64_t salt, void* stage, void* counts_local,
+                      void* position_local, void* spill, void* spill_index, void* spill_count, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    // owner o's block of the staging buffer: [slice][cap] elements
+    std::size_t const elem = keys_only ? sizeof(key_type) : sizeof(slot_type);
+    cuco::b200::exchange_peers blocks{};
+    for (int o = 0; o < num_ranks; ++o) {
+      blocks.base[o] = static_cast<char*>(stage) +
+                       static_cast<std::size_t>(o) * shape.num_regions * shape.segment_capacity * elem;
+    }
+    auto run = [&](auto keys_only_tag, auto first) {
+      eng.template exchange_route_async<decltype(keys_only_tag)::value>(
+        first, n, to_plan(shape), num_ranks, my_rank, salt, blocks, cuco::b200::exchange_peers{},
+        cuco::b200::exchange_peers{}, static_cast<unsigned int*>(counts_local),
+        static_cast<std::uint32_t*>(position_local), spill, static_cast<std::uint32_t*>(spill_index),
+        static_cast<unsigned int*>(spill_count), handle, sref(s), true);
+    };
+    if (keys_only) {
+      run(std::true_type{}, static_cast<key_type const*>(keys));
+    } else {
+      with_input(keys, values, n, [&](auto first, auto) { run(std::false_type{}, first); });
+    }
+  }
+
+  void exchange_apply(const void* segments, const void* counts_recv, std::uint32_t segment_capacity, int num_ranks,
+                      int group, int groups, int op, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto const* segs  = static_cast<slot_type const*>(segments);
+    auto const* cnts  = static_cast<unsigned int const*>(counts_recv);
+    auto const g      = static_cast<std::uint32_t>(group);
+    auto const gs     = static_cast<std::uint32_t>(groups);
+    if (op < 0) {
+      eng.exchange_apply_async(segs, cnts, segment_capacity, num_ranks, g, gs, handle, cuco::b200::action_insert{},
+                               sref(s));
+      return;
+    }
+    if constexpr (is_map) {
+      auto run = [&](auto functor) {
+        eng.exchange_apply_async(segs, cnts, segment_capacity, num_ranks, g, gs, handle,
+                                 cuco::b200::action_apply<decltype(functor), false>{functor}, sref(s));
+      };
+      switch (op) {
+        case 0: run(cuco::reduce::plus{}); break;
+        case 1: run(cuco::reduce::min{}); break;
+        case 2: run(cuco::reduce::max{}); break;
+        default: throw std::invalid_argument("unknown reduce op");
+      }
+    } else {
+      throw std::invalid_argument("insert_or_apply is a static_map operation");
+    }
+  }
+
+  std::uint32_t exchange_fine_regions(int num_ranks) override
+  {
+    return c_.b200_engine().exchange_fine_regions(num_ranks);
+  }
+
+  void exchange_probe(const void* segments, const void* counts_recv, std::uint32_t num_regions,
+                      std::uint32_t segment_capacity, int num_ranks, std::uint32_t region_begin,
+                      std::uint32_t region_count, int op, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto const* segs  = static_cast<slot_type const*>(segments);
+    auto const* cnts  = static_cast<unsigned int const*>(counts_recv);
+    if (op < 0) {
+      eng.exchange_probe_async(segs, cnts, num_regions, segment_capacity, num_ranks, region_begin, region_count,
+                               handle, cuco::b200::action_insert{}, sref(s));
+      return;
+    }
+    if constexpr (is_map) {
+      auto run = [&](auto functor) {
+        eng.exchange_probe_async(segs, cnts, num_regions, segment_capacity, num_ranks, region_begin, region_count,
+                                 handle, cuco::b200::action_apply<decltype(functor), false>{functor}, sref(s));
+      };
+      switch (op) {
+        case 0: run(cuco::reduce::plus{}); break;
+        case 1: run(cuco::reduce::min{}); break;
+        case 2: run(cuco::reduce::max{}); break;
+        default: throw std::invalid_argument("unknown reduce op");
+      }
+    } else {
+      throw std::invalid_argument("insert_or_apply is a static_map operation");
+    }
+  }
+
+  void exchange_lookup_local(const void* segments, const void* counts_recv, void* results,
+                             std::uint32_t segment_capacity, int num_ranks, int what, void* s) override
+  {
+    auto& eng         = c_.b200_engine();
+    auto const handle = typename engine_t::engine_handle{eng.make_engine()};
+    auto const* segs  = static_cast<key_type const*>(segments);
+    auto const* cnts  = static_cast<unsigned int const*>(counts_recv);
+    if (what == 0) {
+      eng.exchange_lookup_local_async(segs, cnts, static_cast<payload_t*>(results), segment_capacity, num_ranks,
+                                      handle, eng.make_find_emit(), sref(s));
+    } else {
+      eng.exchange_lookup_local_async(segs, cnts, static_cast<std::uint8_t*>(results), segment_capacity, num_ranks,
+                                      handle, cuco::b200::emit_present{}, sref(s));
     }
   }
 

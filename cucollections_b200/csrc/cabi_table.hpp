@@ -51,6 +51,21 @@ struct cuco_b200_table {
                                int my_rank, int what, void* stream) = 0;
   virtual void exchange_unpermute(const void* results, const void* position_local, std::int64_t n,
                                   void* out, int what, void* stream) = 0;
+  // ---- staged exchange: local grouping, copy-engine transfers, slice-wise apply ----
+  virtual exchange_shape stage_plan(std::int64_t n_max, int num_ranks, int groups) = 0;
+  virtual void exchange_stage(const void* keys, const void* values, std::int64_t n, bool keys_only,
+                              exchange_shape shape, int num_ranks, int my_rank, std::uint64_t salt,
+                              void* stage, void* counts_local, void* position_local, void* spill,
+                              void* spill_index, void* spill_count, void* stream) = 0;
+  virtual void exchange_apply(const void* segments, const void* counts_recv, std::uint32_t segment_capacity,
+                              int num_ranks, int group, int groups, int op, void* stream) = 0;
+  virtual std::uint32_t exchange_fine_regions(int num_ranks) = 0;
+  virtual void exchange_probe(const void* segments, const void* counts_recv, std::uint32_t num_regions,
+                              std::uint32_t segment_capacity, int num_ranks, std::uint32_t region_begin,
+                              std::uint32_t region_count, int op, void* stream) = 0;
+  virtual void exchange_lookup_local(const void* segments, const void* counts_recv, void* results,
+                                     std::uint32_t segment_capacity, int num_ranks, int what,
+                                     void* stream) = 0;
 };
 
 // Factory signature every cabi_kind.cu instance exports (C++ linkage, hidden from the C ABI).

@@ -35,7 +35,7 @@ from . import _cabi
 from .containers import static_map
 
 DEFAULT_SALT = 0x9E3779B97F4A7C15
-DEFAULT_ROUTING = "fused"  # "staged" | "fused" | "nccl"; CUCO_B200_ROUTING overrides
+DEFAULT_ROUTING = "staged"  # "staged" | "fused" | "nccl"; CUCO_B200_ROUTING overrides
 
 
 def _vp(t):
@@ -291,6 +291,401 @@ class FusedExchange:
         return torch.cat(spilled_keys), torch.cat(spilled_at)
 
 
+class SymmTransport:
+    """Symmetric-memory buffer of the staged exchange: every rank can address every peer's copy
+    (NVLink peer mappings), and a device-side barrier over the group's signal pads."""
+
+    def __init__(self, group, device):
+        self.group, self.device = group, torch.device(device)
+        self.P, self.me = dist.get_world_size(group), dist.get_rank(group)
+        self.hdl = None
+
+    def allocate(self, nbytes):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group if self.group is not None else dist.group.WORLD)
+        return self.buf
+
+    def peer_ptrs(self):
+        return [int(p) for p in self.hdl.buffer_ptrs]
+
+    def barrier(self, channel):
+        self.hdl.barrier(channel=channel)
+
+    def ready(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+
+class StagedExchange:
+    """Exchange of the hash-partitioned table with the transfer on the copy engines (C ABI
+    cuco_b200_exchange_stage / _publish / _copy_async / _apply / _lookup_local / _unpermute).
+
+    Mutations: ONE kernel groups the local batch by (owner, table slice) into a local staging buffer;
+    the copy engines then deliver slice after slice to the owners over NVLink while the owners apply
+    the slices that have already landed - each slice is a dense batch confined to 1/G of the shard, so
+    the owner's L2-blocked path (regroup by 16 MB region, probe region by region) runs on it at full
+    density. Transfer and probe overlap without competing for SMs, and nothing depends on a fixed
+    number of (owner, region) buckets, so shards of any size (C4: 16 - 64 GB) take the same path.
+
+    Lookups: the batch is cut into `lanes` chunks; per chunk the keys are grouped by owner (recording
+    where each answer will come back), copied to the owners, answered there into a local buffer in
+    arrival order, copied back and un-permuted; the chunks are software-pipelined so the copy engines
+    move chunk c + 1 in and chunk c - 1 back while the SMs answer chunk c.
+
+    `transport` supplies the peer-addressable buffer and the cross-rank barrier (SymmTransport; the
+    one-GPU tests plug in simulated ranks)."""
+
+    def __init__(self, table, n_max, group, device, salt, slices=None, lanes=None, transport=None, mode=None):
+        self.table, self.lib, self.device, self.salt = table, table._lib, torch.device(device), salt
+        self.t = transport or SymmTransport(group, device)
+        self.P, self.me = self.t.P, self.t.me
+        self.n_max = int(n_max)
+        k = table.kind
+        self.key_bytes = k.key.itemsize
+        self.slot_bytes = self.key_bytes + (k.value.itemsize if k.value is not None else 0)
+        self.result_bytes = 8
+        shard_bytes = table.capacity() * self.slot_bytes
+        explicit_slices = slices or int(os.environ.get("CUCO_B200_EXCHANGE_SLICES", "0"))
+        if slices is None:
+            slices = explicit_slices or max(1, min(16, shard_bytes // (384 << 20)))
+        if lanes is None:
+            lanes = int(os.environ.get("CUCO_B200_EXCHANGE_LANES", "0")) or max(1, min(4, self.n_max // (1 << 22)))
+        self.G, self.L = int(slices), int(lanes)
+        self.n_lane = -(-self.n_max // self.L)
+        # Mutations, two modes. fine: the SOURCE groups by (owner, L2 region of the owner's shard), the
+        # owner probes the received segments region by region and never regroups - possible while
+        # ranks x regions fits the router's bucket budget (shards up to a few GB). coarse: the source groups
+        # by (owner, one of G table slices) and the owner runs its L2-blocked path (regroup + probe) on
+        # each slice as it lands - any shard size. B = buckets per owner of the staging buffer.
+        mode = mode or os.environ.get("CUCO_B200_EXCHANGE_MODE", "auto")
+        fine = C.c_uint32(0)
+        if mode != "coarse":
+            self.lib.check(self.lib.exchange_fine_regions(table._handle, self.P, C.byref(fine)))
+            if mode == "fine" and fine.value == 0:
+                raise ValueError("shard too large for the fine mode of the staged exchange")
+        self.fine = fine.value != 0
+        self.B = fine.value if self.fine else self.G
+        if self.fine:
+            self.G = max(1, min(explicit_slices or 8, self.B))  # transfer phases (groups of consecutive regions)
+        cap, spill = C.c_uint32(), C.c_uint32()
+        self.lib.check(self.lib.exchange_stage_plan(table._handle, self.n_max, self.P, self.B, C.byref(cap), C.byref(spill)))
+        self.cap, self.spill_cap = cap.value, spill.value
+        self.lib.check(self.lib.exchange_stage_plan(table._handle, self.n_lane, self.P, 1, C.byref(cap), C.byref(spill)))
+        self.cap_l, self.spill_cap_l = cap.value, spill.value
+        P, G, L = self.P, self.B, self.L  # G: buckets per owner in the buffer layouts below
+
+        def pad(x):
+            return (x + 255) // 256 * 256
+
+        # ---- peer-addressable part (identical layout on every rank) ----
+        self.off_recv = 0             # coarse: [slice][source][cap] slot images; fine: [source][region][cap]
+        self.off_counts = self.off_recv + pad(G * P * self.cap * self.slot_bytes)      # [G][P] uint32
+        self.off_flags = self.off_counts + pad(G * P * 4)                   # [P] uint32: spill counts of mutations
+        self.off_keys = self.off_flags + pad(P * 4)                         # L x [P][cap_l] keys
+        self.keys_lane = pad(P * self.cap_l * self.key_bytes)
+        self.off_kcounts = self.off_keys + L * self.keys_lane               # L x [P] uint32
+        self.off_kflags = self.off_kcounts + L * pad(P * 4)                 # L x [P] uint32
+        self.off_back = self.off_kflags + L * pad(P * 4)                    # L x [P][cap_l] results (8 bytes each)
+        self.back_lane = pad(P * self.cap_l * self.result_bytes)
+        total = self.off_back + L * self.back_lane
+        self.buf = self.t.allocate(total)
+        self.base = self.buf.data_ptr()
+        self.buf[self.off_counts:self.off_keys].zero_()
+        self.buf[self.off_kcounts:self.off_back].zero_()
+        # ---- local part ----
+        dev = self.device
+        self.stage = torch.empty(P * G * self.cap * self.slot_bytes, dtype=torch.uint8, device=dev)
+        self.counts_local = torch.zeros(P * G, dtype=torch.int32, device=dev)
+        self.spill = torch.empty(self.spill_cap * self.slot_bytes, dtype=torch.uint8, device=dev)
+        self.spill_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.position_local = torch.empty(max(1, self.n_max), dtype=torch.int32, device=dev)
+        self.lanes = []
+        for i in range(L):
+            lane = _Lane()
+            lane.id = i
+            lane.stage = torch.empty(P * self.cap_l * self.key_bytes, dtype=torch.uint8, device=dev)
+            lane.counts_local = torch.zeros(P, dtype=torch.int32, device=dev)
+            lane.results = torch.empty(P * self.cap_l * self.result_bytes, dtype=torch.uint8, device=dev)
+            lane.spill = torch.empty(self.spill_cap_l * self.key_bytes, dtype=torch.uint8, device=dev)
+            lane.spill_index = torch.empty(self.spill_cap_l, dtype=torch.int32, device=dev)
+            lane.spill_count = torch.zeros(1, dtype=torch.int32, device=dev)
+            lane.staged, lane.landed, lane.answered, lane.returned = (torch.cuda.Event() for _ in range(4))
+            self.lanes.append(lane)
+        self.flags_host = torch.zeros((1 + L) * P, dtype=torch.int32).pin_memory()
+        # high priority: the tiny barrier / publish kernels on these streams must not queue behind the
+        # probe kernels' CTAs, or a landed slice would be announced late
+        self.copy_in = torch.cuda.Stream(dev, priority=-1)    # source -> owner transfers
+        self.copy_back = torch.cuda.Stream(dev, priority=-1)  # owner -> source transfers (lookup results)
+        self.staged = torch.cuda.Event()
+        self.consumed = torch.cuda.Event()
+        self.slice_landed = [torch.cuda.Event() for _ in range(self.G)]
+        self.consumed.record(torch.cuda.current_stream(dev))
+        self._peers = None
+        self.trace = [] if os.environ.get("CUCO_B200_EXCHANGE_TRACE") else None
+        self.t.ready()
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def launches_per_step(self) -> int:
+        # insert = stage + publish + G x (probe [+ regroup in coarse mode]); find = lanes x (stage + publish +
+        # lookup + unpermute)
+        return 2 + (1 if self.fine else 2) * self.G + 4 * self.L
+
+    def _tick(self, label, stream=None):
+        """CUCO_B200_EXCHANGE_TRACE=1: a timing event on `stream`; trace_summary() reports every label as
+        milliseconds since the call's "begin" (median over the traced calls), i.e. the pipeline as it ran."""
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream or torch.cuda.current_stream(self.device))
+            if label == "begin":
+                self.trace.append([])
+            self.trace[-1].append((label, e))
+
+    def trace_summary(self):
+        if not self.trace:
+            return {}
+        torch.cuda.synchronize(self.device)
+        samples = {}
+        for call in self.trace[1:] or self.trace:  # the first call is a warm-up when there are more
+            for label, e in call[1:]:
+                samples.setdefault(label, []).append(call[0][1].elapsed_time(e))
+        return {k: round(statistics.median(v), 3) for k, v in samples.items()}
+
+    def peers(self):
+        if self._peers is None:
+            self._peers = self.t.peer_ptrs()
+        return self._peers
+
+    def _ptr_array(self, offset):
+        return (C.c_void_p * self.P)(*[p + offset for p in self.peers()])
+
+    def _s(self, stream=None):
+        return C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+
+    def _copy(self, dst, src, nbytes, stream):
+        self.lib.check(self.lib.copy_async(C.c_void_p(dst), C.c_void_p(src), nbytes, self._s(stream)))
+
+    # ---- mutations: the steps (driven in lock-step by the simulated-rank tests) --------------------
+    def stage_pairs(self, pairs):
+        n = pairs.shape[0]
+        if n > self.n_max:
+            raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_stage(
+                self.table._handle, _vp(pairs), None, n, 0, self.B, self.cap, self.spill_cap, self.P, self.me,
+                self.salt, _vp(self.stage), _vp(self.counts_local), None, _vp(self.spill), None,
+                _vp(self.spill_count), self._s()))
+
+    def publish_pairs(self, stream=None):
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_publish(
+                _vp(self.counts_local), _vp(self.spill_count), self._ptr_array(self.off_counts),
+                self._ptr_array(self.off_flags), self.B, self.cap, self.P, self.me, int(self.fine),
+                self._s(stream)))
+
+    def _buckets(self, g):
+        """Buckets (table slices, or L2 regions in fine mode) that travel in phase g."""
+        return (g * self.B // self.G, (g + 1) * self.B // self.G)
+
+    def send_slice(self, g, stream=None):
+        """Phase g: this rank's blocks for every owner -> the owner's receive buffer, owners in
+        rank-rotated order (at any moment every rank writes to a different peer)."""
+        block = self.cap * self.slot_bytes
+        b0, b1 = self._buckets(g)
+        for i in range(self.P):
+            o = (self.me + i) % self.P
+            src = self.stage.data_ptr() + (o * self.B + b0) * block
+            if self.fine:   # recv[source][region][cap]
+                dst = self.peers()[o] + self.off_recv + (self.me * self.B + b0) * block
+            else:           # recv[slice][source][cap], one slice per phase
+                dst = self.peers()[o] + self.off_recv + (b0 * self.P + self.me) * block
+            with torch.cuda.device(self.device):
+                self._copy(dst, src, (b1 - b0) * block, stream)
+
+    def apply_slice(self, g, reduce_op=-1):
+        block = self.cap * self.slot_bytes
+        b0, b1 = self._buckets(g)
+        with torch.cuda.device(self.device):
+            if self.fine:
+                self.lib.check(self.lib.exchange_probe(
+                    self.table._handle, C.c_void_p(self.base + self.off_recv), C.c_void_p(self.base + self.off_counts),
+                    self.B, self.cap, self.P, b0, b1 - b0, reduce_op, self._s()))
+            else:
+                self.lib.check(self.lib.exchange_apply(
+                    self.table._handle, C.c_void_p(self.base + self.off_recv + g * self.P * block),
+                    C.c_void_p(self.base + self.off_counts + g * self.P * 4), self.cap, self.P, g, self.G,
+                    reduce_op, self._s()))
+
+    def mutate(self, pairs, reduce_op=-1):
+        """Routes and applies a batch of [n, 2] pairs; returns this rank's spilled pairs (or None)."""
+        main = torch.cuda.current_stream(self.device)
+        self._tick("begin")
+        self.stage_pairs(pairs)
+        self.staged.record(main)
+        self._tick("mutate: staged")
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.staged)
+            self.copy_in.wait_event(self.consumed)   # this rank's previous exchange has been applied
+            self.t.barrier(0)                        # ... and so has everybody else's: the buffers are free
+            self.publish_pairs(self.copy_in)
+            for g in range(self.G):
+                self.send_slice(g, self.copy_in)
+                self.t.barrier(0)                    # slice g has landed on every owner
+                self.slice_landed[g].record(self.copy_in)
+                self._tick(f"mutate: slice {g} landed", self.copy_in)
+        for g in range(self.G):
+            main.wait_event(self.slice_landed[g])
+            self.apply_slice(g, reduce_op)
+            self._tick(f"mutate: slice {g} applied")
+        self.consumed.record(main)
+        total, mine = self._spilled(mutation=True)
+        if total == 0:
+            return None
+        m = mine[0]
+        return self.spill[: m * self.slot_bytes].view(pairs.dtype).view(m, 2)
+
+    # ---- lookups ---------------------------------------------------------------------------------
+    def _chunks(self, n):
+        return [(lo, min(n, lo + self.n_lane)) for lo in range(0, n, self.n_lane)] or [(0, 0)]
+
+    def stage_keys(self, lane, keys, lo):
+        n = keys.shape[0]
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_stage(
+                self.table._handle, _vp(keys), None, n, 1, 1, self.cap_l, self.spill_cap_l, self.P, self.me,
+                self.salt, _vp(lane.stage), _vp(lane.counts_local), _vp(self.position_local[lo:lo + max(n, 1)]),
+                _vp(lane.spill), _vp(lane.spill_index), _vp(lane.spill_count), self._s()))
+
+    def send_keys(self, lane, stream=None):
+        pad4 = (self.P * 4 + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_publish(
+                _vp(lane.counts_local), _vp(lane.spill_count), self._ptr_array(self.off_kcounts + lane.id * pad4),
+                self._ptr_array(self.off_kflags + lane.id * pad4), 1, self.cap_l, self.P, self.me, 0,
+                self._s(stream)))
+            block = self.cap_l * self.key_bytes
+            for i in range(self.P):
+                o = (self.me + i) % self.P
+                self._copy(self.peers()[o] + self.off_keys + lane.id * self.keys_lane + self.me * block,
+                           lane.stage.data_ptr() + o * block, block, stream)
+
+    def answer_keys(self, lane, what):
+        pad4 = (self.P * 4 + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_lookup_local(
+                self.table._handle, C.c_void_p(self.base + self.off_keys + lane.id * self.keys_lane),
+                C.c_void_p(self.base + self.off_kcounts + lane.id * pad4), _vp(lane.results), self.cap_l, self.P,
+                what, self._s()))
+
+    def return_results(self, lane, what, stream=None):
+        rbytes = self._result_bytes(what)
+        block = self.cap_l * rbytes
+        with torch.cuda.device(self.device):
+            for i in range(self.P):
+                s = (self.me + i) % self.P
+                self._copy(self.peers()[s] + self.off_back + lane.id * self.back_lane + self.me * block,
+                           lane.results.data_ptr() + s * block, block, stream)
+
+    def _result_bytes(self, what):
+        k = self.table.kind
+        return 1 if what == 1 else (k.value.itemsize if k.value is not None else k.key.itemsize)
+
+    def unpermute(self, lane, what, out, lo, hi):
+        with torch.cuda.device(self.device):
+            self.lib.check(self.lib.exchange_unpermute(
+                self.table._handle, C.c_void_p(self.base + self.off_back + lane.id * self.back_lane),
+                _vp(self.position_local[lo:lo + max(hi - lo, 1)]), hi - lo, _vp(out[lo:hi]), what, self._s()))
+
+    def lookup(self, keys, out, what):
+        """what: 0 find, 1 contains. Returns (spilled keys, their source indices) or None."""
+        n = keys.shape[0]
+        if n > self.n_max:
+            raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
+        main = torch.cuda.current_stream(self.device)
+        # every rank runs all L lanes in every call (empty chunks included): the barriers must match
+        chunks = self._chunks(n)
+        chunks += [(n, n)] * (self.L - len(chunks))
+
+        def stage(c):
+            lo, hi = chunks[c]
+            self.stage_keys(self.lanes[c], keys[lo:hi], lo)
+            self.lanes[c].staged.record(main)
+            self._tick(f"lookup: chunk {c} staged")
+
+        def transfer_in(c):
+            lane = self.lanes[c]
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(lane.staged)
+                if c == 0:
+                    self.copy_in.wait_event(self.consumed)
+                    self.t.barrier(1)                 # every rank is done with the previous lookup's buffers
+                self.send_keys(lane, self.copy_in)
+                self.t.barrier(1)                     # chunk c has landed on every owner
+                lane.landed.record(self.copy_in)
+                self._tick(f"lookup: chunk {c} landed", self.copy_in)
+
+        def transfer_back(c):
+            lane = self.lanes[c]
+            with torch.cuda.stream(self.copy_back):
+                self.copy_back.wait_event(lane.answered)
+                self.return_results(lane, what, self.copy_back)
+                self.t.barrier(2)                     # every owner has returned this rank's answers of chunk c
+                lane.returned.record(self.copy_back)
+                self._tick(f"lookup: chunk {c} returned", self.copy_back)
+
+        self._tick("begin")
+        stage(0)
+        transfer_in(0)
+        for c in range(self.L):
+            if c + 1 < self.L:
+                stage(c + 1)
+                transfer_in(c + 1)
+            lane = self.lanes[c]
+            main.wait_event(lane.landed)
+            self.answer_keys(lane, what)
+            lane.answered.record(main)
+            self._tick(f"lookup: chunk {c} answered")
+            transfer_back(c)
+            if c >= 1:
+                main.wait_event(self.lanes[c - 1].returned)
+                self.unpermute(self.lanes[c - 1], what, out, *chunks[c - 1])
+                self._tick(f"lookup: chunk {c - 1} unpermuted")
+        last = self.L - 1
+        main.wait_event(self.lanes[last].returned)
+        self.unpermute(self.lanes[last], what, out, *chunks[last])
+        self._tick(f"lookup: chunk {last} unpermuted")
+        self.consumed.record(main)
+        total, mine = self._spilled(mutation=False)
+        if total == 0:
+            return None
+        parts = [(c, m) for c, m in enumerate(mine) if m]
+        if not parts:
+            return keys[:0], torch.empty(0, dtype=torch.int64, device=self.device)
+        spilled_keys = [self.lanes[c].spill[: m * self.key_bytes].view(keys.dtype) for c, m in parts]
+        spilled_at = [self.lanes[c].spill_index[:m].to(torch.int64) + chunks[c][0] for c, m in parts]
+        return torch.cat(spilled_keys), torch.cat(spilled_at)
+
+    def _spilled(self, mutation):
+        """(total spilled over all ranks, [spilled on this rank per buffer set]); one small read-back."""
+        P = self.P
+        pad4 = (P * 4 + 255) // 256 * 256
+        if mutation:
+            views = [self.buf[self.off_flags: self.off_flags + P * 4].view(torch.int32)]
+            caps = [self.spill_cap]
+        else:
+            views = [self.buf[self.off_kflags + i * pad4: self.off_kflags + i * pad4 + P * 4].view(torch.int32)
+                     for i in range(self.L)]
+            caps = [self.spill_cap_l] * self.L
+        host = self.flags_host[: len(views) * P]
+        for i, v in enumerate(views):
+            host[i * P:(i + 1) * P].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        mine = [int(host[i * P + self.me].item()) for i in range(len(views))]
+        if any(m > c for m, c in zip(mine, caps)):
+            raise RuntimeError("batch too skewed for the exchange buffers: spill list overflowed")
+        return int(host.sum().item()), mine
+
+
 class partitioned_static_map:
     """static_map<int64,int64> sharded over the ranks of `group` by owner(key)."""
 
@@ -309,6 +704,7 @@ class partitioned_static_map:
         # every shard at or below the requested load factor
         n_local = int(-(-n_total // self.world) * headroom) + 1
         self.table = backend.make_table(n_local, load_factor, **table_kw)
+        self._table_kw, self._scratch, self._scratch_capacity = dict(table_kw), None, 0
         self.fused = None
         self.routing = "nccl"
         if fused_batch:
@@ -370,7 +766,23 @@ class partitioned_static_map:
         new = torch.tensor([self.table.insert(received)], dtype=torch.int64)
         return self._allreduce_sum(new)
 
-    def insert_or_apply(self, pairs, op="plus", init=None):
+    def insert_or_apply(self, pairs, op="plus", init=None, pre_aggregate=None):
+        """payload[key] = fold of `op` over every rank's rows carrying key.
+
+        `pre_aggregate` = capacity hint (distinct keys this rank may see): the rows are first folded into
+        a rank-local scratch table (reference idea: insert_or_apply_shmem, static_map/kernels.cuh:171-264,
+        one level up - the whole GPU instead of one block), and only its <= `pre_aggregate` partial
+        results cross NVLink. op must be associative and commutative (plus / min / max are)."""
+        if pre_aggregate:
+            if self._scratch is None or self._scratch_capacity < pre_aggregate:
+                if self._scratch is not None:
+                    self._scratch.close()
+                self._scratch = self.backend.make_table(int(pre_aggregate), 0.5, **self._table_kw)
+                self._scratch_capacity = int(pre_aggregate)
+            self._scratch.clear_async()
+            self._scratch.insert_or_apply(pairs, op=op, init=init)
+            keys, vals = self._scratch.retrieve_all()
+            pairs = torch.stack([keys, vals], dim=1).contiguous()
         if self.fused is not None and init is None:
             pairs = self.fused.mutate(pairs, {"plus": _cabi.PLUS, "min": _cabi.MIN, "max": _cabi.MAX}[op])
             if pairs is None:
@@ -423,6 +835,9 @@ class partitioned_static_map:
 
     def close(self):
         self.table.close()
+        if self._scratch is not None:
+            self._scratch.close()
+            self._scratch = None
 
 
 # ==================================================================================================
@@ -554,6 +969,72 @@ def _c4_leg(args, lib, dev, rank, world, routing):
     if not all(result["properties"].values()):
         raise AssertionError(f"C4 leg failed its properties: {result}")
     return result
+
+
+def _c5_leg(args, lib, dev, rank, world, routing):
+    """BASELINE configs[4]: group-by aggregate, insert_or_apply(plus) of 2 B rows with 10 M distinct keys
+    (uniform_int[1, 1e7], value 1, empty value 0: benchmarks/static_map/insert_or_apply_bench.cu:59) into the
+    partitioned static_map<int64,int64>, measured both ways: every row routed to its owner, and rows folded
+    into a rank-local scratch table first so that only <= 10 M partial sums per rank cross NVLink. Both
+    results are compared bit-exactly with each other and with the all-reduced histogram of the rows."""
+    stream = torch.cuda.current_stream(dev)
+    rows_total = args.c5_rows or 2_000_000_000
+    distinct = args.c5_distinct or 10_000_000
+    share = rows_total // world
+    batch = min(share, 250_000_000)
+    batches = -(-share // batch)
+
+    def make(b):
+        m = min(batch, share - b * batch)
+        g = torch.Generator(device=dev).manual_seed(5000 + 64 * b + rank)
+        k = torch.randint(1, distinct + 1, (m,), generator=g, device=dev, dtype=torch.int64)
+        return torch.stack([k, torch.ones_like(k)], dim=1).contiguous()
+
+    probe = torch.arange(0, distinct + 8, device=dev, dtype=torch.int64)
+    hist = torch.zeros(distinct + 8, dtype=torch.int64, device=dev)
+    for b in range(batches):
+        p = make(b)
+        hist += torch.bincount(p[:, 0], minlength=distinct + 8)
+        del p
+    dist.all_reduce(hist)
+    out = {}
+    for name, hint in (("every_row_routed", None), ("pre_aggregated_per_gpu", distinct)):
+        n_max = batch if hint is None else min(batch, distinct + distinct // 8)
+        table = partitioned_static_map(distinct, 0.5, backend=GpuBackend(dev, lib),
+                                       fused_batch=n_max if routing != "nccl" else None, routing=routing,
+                                       empty_value=0, probing="linear_probing", cg_size=1)
+        times = []
+        for rep in range(3):  # the first repetition is the warm-up
+            table.clear_async()
+            total = 0.0
+            for b in range(batches):
+                p = make(b)
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                table.insert_or_apply(p, op="plus", pre_aggregate=hint)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                total += e0.elapsed_time(e1)
+                del p
+            times.append(total)
+        ms = _max_over_ranks([min(times[1:]), statistics.median(times[1:])], dev)
+        sums = table.find(probe)
+        size = table.size()
+        exact = torch.tensor([int(torch.equal(sums, hist))], dtype=torch.int64, device=dev)
+        dist.all_reduce(exact, op=dist.ReduceOp.MIN)
+        out[name] = {"ms_best": ms[0], "ms_median": ms[1], "grows_per_s": share * world / (ms[1] * 1e-3) / 1e9,
+                     "size": size, "sums_equal_histogram_of_rows": bool(exact.item()),
+                     "rows_counted": int(sums.sum().item())}
+        table.close()
+        torch.cuda.empty_cache()
+        if not (out[name]["sums_equal_histogram_of_rows"] and out[name]["rows_counted"] == share * world):
+            raise AssertionError(f"C5 leg ({name}) lost or double-counted rows: {out[name]}")
+    out["workload"] = (f"hash-partitioned static_map<int64,int64> insert_or_apply(plus), {share * world} rows "
+                       f"({share} per GPU in {batches} bulk calls), {distinct} distinct keys, {world} GPUs")
+    out["unit"] = "G rows/s"
+    return out
 
 
 def bench(args, lib, impl, clock_sampler=None, parity_gate=None):
@@ -693,5 +1174,8 @@ def bench(args, lib, impl, clock_sampler=None, parity_gate=None):
     if impl == "native" and not getattr(args, "no_c4", False):
         result["c4"] = _c4_leg(args, lib, dev, rank, world, routing)
         result["config"]["c4_workload"] = result["c4"]["workload"]
+    if impl == "native" and not getattr(args, "no_c5", False):
+        result["c5"] = _c5_leg(args, lib, dev, rank, world, routing)
+        result["config"]["c5_workload"] = result["c5"]["workload"]
     dist.barrier()
     return result

@@ -24,6 +24,7 @@
 // instantiations); otherwise the defaults below are the only instantiations.
 #pragma once
 
+#include <cuco/b200/blocked_match.cuh>
 #include <cuco/b200/bulk_kernels.cuh>
 #include <cuco/b200/match_kernels.cuh>
 #include <cuco/b200/probe_engine.cuh>
@@ -353,10 +354,7 @@ class table_engine {
     this->clear_async(stream);
   }
 
-  ~table_engine()
-  {
-    if (pool_ != nullptr) { cudaMemPoolDestroy(pool_); }
-  }
+  ~table_engine() = default;
   table_engine(table_engine const&)            = delete;
   table_engine& operator=(table_engine const&) = delete;
 
@@ -480,9 +478,9 @@ class table_engine {
     auto in           = unwrap(first);
     auto const engine = ref.engine();
     using engine_t    = std::decay_t<decltype(engine)>;
-    // one key per thread, one CTA per 256 keys (random probes: the hardware scheduler balances them)
+    // two keys per thread, one CTA per 512 keys (random probes: the hardware scheduler balances them)
     auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
-      cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
+      cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size} * 2), 0x7fffffff));
     if (this->fast_path_ok(false)) {
       erase_kernel<block_size, engine_t::sector_chunk_slots>
         <<<grid, block_size, 0, stream.get()>>>(in, n, engine);
@@ -552,6 +550,10 @@ class table_engine {
     using engine_t    = std::decay_t<decltype(engine)>;
     auto* counter     = this->zeroed_counter(stream);
     auto const grid   = generic_grid(n);
+    if (this->blocked_matches<IsOuter, true>(in, n, static_cast<value_type*>(nullptr),
+                                             static_cast<value_type*>(nullptr), counter, engine, stream)) {
+      return this->read_counter(counter, stream);
+    }
     if (this->fast_path_ok(false)) {
       auto const table_bytes = static_cast<std::size_t>(storage_.capacity()) * sizeof(value_type);
       auto const depth = table_bytes >= tuning().count_ahead_min_table ? tuning().count_ahead : 1;
@@ -586,6 +588,9 @@ class table_engine {
     auto const engine = ref.engine();
     using engine_t    = std::decay_t<decltype(engine)>;
     auto* counter     = this->zeroed_counter(stream);
+    if (this->blocked_matches<IsOuter, false>(in, n, out_probe, out_match, counter, engine, stream)) {
+      return this->read_counter(counter, stream);
+    }
     // one CTA per round of 256 keys (like the other random-probe kernels)
     auto const grid = static_cast<unsigned>(std::min<cuco::detail::index_type>(
       cuco::detail::int_div_ceil(n, cuco::detail::index_type{block_size}), 0x7fffffff));
@@ -599,6 +604,140 @@ class table_engine {
         <<<grid, block_size, 0, stream.get()>>>(in, n, out_probe, out_match, counter, engine);
     }
     return this->read_counter(counter, stream);
+  }
+
+  /// L2-blocked count / retrieve (blocked_match.cuh) for probe batches that are a plain, 16-byte
+  /// aligned array of keys over a table much larger than L2: stage the keys grouped by table region,
+  /// then probe region by region. Returns false - nothing launched, the caller takes the direct
+  /// kernels - when the path does not apply or scratch memory is not to be had. `IsCount` selects
+  /// the total-only flavour (the output iterators are ignored).
+  template <bool IsOuter,
+            bool IsCount,
+            typename InputIt,
+            typename OutputProbeIt,
+            typename OutputMatchIt,
+            typename EngineT>
+  [[nodiscard]] bool blocked_matches(InputIt in,
+                                     cuco::detail::index_type n,
+                                     OutputProbeIt out_probe,
+                                     OutputMatchIt out_match,
+                                     size_type* counter,
+                                     EngineT const& engine,
+                                     cuda::stream_ref stream) const
+  {
+    using cuco::detail::index_type;
+    if constexpr (!std::is_pointer_v<InputIt>) {
+      return false;
+    } else if constexpr (!std::is_same_v<std::remove_cv_t<std::remove_pointer_t<InputIt>>, key_type> ||
+                         !(sizeof(key_type) == 4 || sizeof(key_type) == 8)) {
+      return false;
+    } else {
+      auto const& t          = tuning();
+      auto const capacity    = static_cast<std::uint64_t>(storage_.capacity());
+      auto const table_bytes = capacity * sizeof(value_type);
+      if (t.blocked == 0 || !this->fast_path_ok(false) || (reinterpret_cast<std::uintptr_t>(in) % 16) != 0) {
+        return false;
+      }
+      if (table_bytes / route_max_regions > (std::size_t{64} << 20) || n >= (index_type{1} << 31)) { return false; }
+      // auto mode: every probe fetches a 128-byte line of a table well beyond L2; grouping pays once
+      // the batch touches the table about once per line or denser
+      if (t.blocked < 0 && !(table_bytes >= t.blocked_min_table && n >= t.blocked_min_elements &&
+                             static_cast<std::uint64_t>(n) * 128 >= table_bytes)) {
+        return false;
+      }
+      auto const num_regions = static_cast<std::uint32_t>(std::min<std::uint64_t>(
+        route_max_regions, std::max<std::uint64_t>(2, (table_bytes + t.region_bytes - 1) / t.region_bytes)));
+      auto const mean = (static_cast<std::uint64_t>(n) + num_regions - 1) / num_regions;
+      auto const cap  = static_cast<std::uint32_t>((mean + mean / 16 + 1024 + 15) / 16 * 16);
+      auto const spill_capacity =
+        static_cast<std::uint32_t>(std::max<std::uint64_t>(65536, static_cast<std::uint64_t>(n) / 8));
+      std::size_t const counts_bytes = (((num_regions + 1) * sizeof(unsigned int)) + 255) / 256 * 256;
+      std::size_t const staged_bytes = (static_cast<std::size_t>(num_regions) * cap * sizeof(key_type) + 255) / 256 * 256;
+      auto* base = static_cast<char*>(this->scratch_alloc(
+        counts_bytes + staged_bytes + static_cast<std::size_t>(spill_capacity) * sizeof(key_type), stream.get()));
+      if (base == nullptr) { return false; }
+      auto* counts      = reinterpret_cast<unsigned int*>(base);  // [num_regions] fills, then the spill count
+      auto* spill_count = counts + num_regions;
+      auto* segments    = reinterpret_cast<key_type*>(base + counts_bytes);
+      auto* spill       = reinterpret_cast<key_type*>(base + counts_bytes + staged_bytes);
+      constexpr int chunk = EngineT::sector_chunk_slots;
+
+      // ---- pass 1: group the probe keys by region ----
+      using stencil_t   = thrust::constant_iterator<bool>;
+      auto const router = tile_route_kernel<tile_route_block_size,
+                                            chunk,
+                                            false,
+                                            stencil_t,
+                                            always_true,
+                                            size_type,
+                                            EngineT,
+                                            action_insert,
+                                            region_spill_router,
+                                            key_type>;
+      auto const smem = tile_route_smem_bytes<tile_route_block_size, key_type>(num_regions);
+      if (!opt_in_dynamic_smem(router, std::size_t{200} << 10)) {
+        this->scratch_free(base, stream.get());
+        return false;
+      }
+      cudaMemsetAsync(counts, 0, (num_regions + 1) * sizeof(unsigned int), stream.get());
+      {
+        auto const tiles = cuco::detail::int_div_ceil(n, index_type{tile_route_block_size} * route_items_per_thread);
+        int per_sm       = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, router, tile_route_block_size, smem);
+        auto const resident = std::max(1, per_sm) * cuco::detail::multiprocessor_count();
+        auto const grid     = static_cast<unsigned>(std::min<index_type>(tiles, resident));
+        region_spill_router route{};
+        route.regions = region_map::over(capacity, num_regions);
+        router<<<grid, tile_route_block_size, smem, stream.get()>>>(
+          in, n, stencil_t{true}, always_true{}, segments, counts, route, cap, static_cast<size_type*>(nullptr),
+          engine, action_insert{}, route_spill{spill, spill_count, spill_capacity});
+      }
+
+      // ---- pass 2: probe region by region ----
+      auto const region_slots = (capacity + num_regions - 1) / num_regions;
+      auto const ctas         = static_cast<unsigned>(
+        std::max<index_type>(1, cuco::detail::int_div_ceil(index_type{cap}, index_type{block_size} * 4)));
+      auto const share = (region_slots * sizeof(value_type) + ctas - 1) / ctas;
+      blocked_layout const layout{counts,
+                                  cap,
+                                  region_slots,
+                                  table_bytes,
+                                  t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
+                                  1u};
+      auto direct = [&](key_type const* keys, index_type count) {
+        if constexpr (IsCount) {
+          count_kernel<IsOuter, block_size, chunk, 1>
+            <<<generic_grid(count), block_size, 0, stream.get()>>>(keys, count, counter, engine);
+        } else {
+          auto const grid = static_cast<unsigned>(std::min<index_type>(
+            cuco::detail::int_div_ceil(count, index_type{block_size}), 0x7fffffff));
+          retrieve_kernel<IsOuter, block_size, chunk, 1>
+            <<<grid, block_size, 0, stream.get()>>>(keys, count, out_probe, out_match, counter, engine);
+        }
+      };
+      if constexpr (IsCount) {
+        blocked_count_kernel<IsOuter, block_size, chunk, 1>
+          <<<dim3{ctas, num_regions}, block_size, 0, stream.get()>>>(segments, layout, counter, engine);
+      } else {
+        blocked_retrieve_kernel<IsOuter, block_size, chunk, 1>
+          <<<dim3{ctas, num_regions}, block_size, 0, stream.get()>>>(
+            segments, layout, out_probe, out_match, counter, engine);
+      }
+
+      // ---- keys that did not fit their segment (skewed batches) ----
+      unsigned int spilled = 0;
+      cudaMemcpyAsync(&spilled, spill_count, sizeof(spilled), cudaMemcpyDeviceToHost, stream.get());
+      cudaStreamSynchronize(stream.get());
+      if (spilled > spill_capacity) {
+        // more than the list holds: start over with the direct kernel on the whole batch
+        cudaMemsetAsync(counter, 0, sizeof(size_type), stream.get());
+        direct(in, n);
+      } else if (spilled > 0) {
+        direct(spill, static_cast<index_type>(spilled));
+      }
+      this->scratch_free(base, stream.get());
+      return true;
+    }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -950,28 +1089,47 @@ class table_engine {
   /// callers then take a path that needs none). Returned with `scratch_free` on the same stream.
   [[nodiscard]] void* scratch_alloc(std::size_t bytes, cudaStream_t stream) const noexcept
   {
-    if (pool_ == nullptr) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess) { return nullptr; }
+    auto const pool = scratch_pool();
+    if (pool == nullptr) { return nullptr; }
+    void* p = nullptr;
+    if (cudaMallocFromPoolAsync(&p, bytes, pool, stream) != cudaSuccess) {
+      cudaGetLastError();  // clear the sticky-free error state of the runtime call
+      return nullptr;
+    }
+    return p;
+  }
+
+  /// The stream-ordered pool all containers on the current device draw their per-call scratch from:
+  /// one per device for the life of the process (a pool per container costs a 2 MiB granule and a
+  /// driver round trip each - the reference's shared_memory_test builds 1000 maps). Freed blocks stay
+  /// cached up to CUCO_B200_SCRATCH_KEEP_MIB (default 4096) so that back-to-back bulk calls do not
+  /// pay cudaMalloc; anything above goes back to the driver at the next synchronisation.
+  [[nodiscard]] static cudaMemPool_t scratch_pool() noexcept
+  {
+    constexpr int max_devices = 64;
+    static std::mutex guard;
+    static cudaMemPool_t pools[max_devices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= max_devices) { return nullptr; }
+    std::lock_guard<std::mutex> lock{guard};
+    if (pools[dev] == nullptr) {
       cudaMemPoolProps props{};
       props.allocType     = cudaMemAllocationTypePinned;
       props.handleTypes   = cudaMemHandleTypeNone;
       props.location.type = cudaMemLocationTypeDevice;
       props.location.id   = dev;
-      if (cudaMemPoolCreate(&pool_, &props) != cudaSuccess) {
+      if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) {
         cudaGetLastError();
-        pool_ = nullptr;
+        pools[dev] = nullptr;
         return nullptr;
       }
-      std::uint64_t keep = ~std::uint64_t{0};
-      cudaMemPoolSetAttribute(pool_, cudaMemPoolAttrReleaseThreshold, &keep);
+      std::uint64_t keep = std::uint64_t{4096} << 20;
+      if (char const* s = std::getenv("CUCO_B200_SCRATCH_KEEP_MIB")) {
+        keep = static_cast<std::uint64_t>(std::max(0, std::atoi(s))) << 20;
+      }
+      cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    void* p = nullptr;
-    if (cudaMallocFromPoolAsync(&p, bytes, pool_, stream) != cudaSuccess) {
-      cudaGetLastError();  // clear the sticky-free error state of the runtime call
-      return nullptr;
-    }
-    return p;
+    return pools[dev];
   }
 
   void scratch_free(void* p, cudaStream_t stream) const noexcept
@@ -994,7 +1152,9 @@ class table_engine {
                       size_type* counter,
                       EngineT const& engine,
                       Action action,
-                      cuda::stream_ref stream)
+                      cuda::stream_ref stream,
+                      std::uint64_t first_slot  = 0,
+                      std::uint64_t slice_slots = 0)
   {
     using cuco::detail::index_type;
     // region counters and staged positions are 32-bit: larger batches go through in slices
@@ -1002,7 +1162,8 @@ class table_engine {
     if (n > slice) {
       for (index_type done = 0; done < n; done += slice) {
         auto const len = std::min<index_type>(slice, n - done);
-        if (!this->blocked_mutate<Counted>(in + done, len, stencil + done, pred, counter, engine, action, stream)) {
+        if (!this->blocked_mutate<Counted>(
+              in + done, len, stencil + done, pred, counter, engine, action, stream, first_slot, slice_slots)) {
           if (done == 0) { return false; }
           // later slices without scratch memory: the direct kernel takes them (same results)
           this->direct_mutate<Counted>(in + done, n - done, stencil + done, pred, counter, engine, action, stream);
@@ -1012,7 +1173,9 @@ class table_engine {
       return true;
     }
     auto const& t          = tuning();
-    auto const capacity    = static_cast<std::uint64_t>(storage_.capacity());
+    // the slots the batch can hash to: the whole table, or the slice the caller vouches for (batches
+    // that arrive grouped by table slice, e.g. from the multi-GPU exchange)
+    auto const capacity    = slice_slots != 0 ? slice_slots : static_cast<std::uint64_t>(storage_.capacity());
     auto const table_bytes = capacity * sizeof(value_type);
     auto const num_regions = static_cast<std::uint32_t>(std::min<std::uint64_t>(
       route_max_regions, std::max<std::uint64_t>(2, (table_bytes + t.region_bytes - 1) / t.region_bytes)));
@@ -1030,8 +1193,7 @@ class table_engine {
     auto* segments = reinterpret_cast<value_type*>(base + counts_bytes);
     cudaMemsetAsync(counts, 0, num_regions * sizeof(unsigned int), stream.get());
 
-    unsigned __int128 const scaled = (static_cast<unsigned __int128>(num_regions) << 64) / capacity;
-    region_map const regions{static_cast<std::uint64_t>(scaled) + 1, num_regions};
+    auto const regions = region_map::over(capacity, num_regions, first_slot);
 
     constexpr int chunk = EngineT::sector_chunk_slots;
     // ---- pass 1 ----
@@ -1052,14 +1214,13 @@ class table_engine {
           if (opt_in_dynamic_smem(kernel, std::size_t{200} << 10)) {
             auto const tiles =
               cuco::detail::int_div_ceil(n, index_type{tile_route_block_size} * route_items_per_thread);
-            static int const resident = [&] {
-              int per_sm = 0;
-              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile_route_block_size, smem);
-              return std::max(1, per_sm) * cuco::detail::multiprocessor_count();
-            }();
-            auto const grid = static_cast<unsigned>(std::min<index_type>(tiles, resident));
+            int per_sm = 0;  // depends on the number of regions (bucket arrays live in shared memory)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile_route_block_size, smem);
+            auto const resident = std::max(1, per_sm) * cuco::detail::multiprocessor_count();
+            auto const grid     = static_cast<unsigned>(std::min<index_type>(tiles, resident));
             kernel<<<grid, tile_route_block_size, smem, stream.get()>>>(
-              in, n, stencil, pred, segments, counts, regions, segment_capacity, counter, engine, action);
+              in, n, stencil, pred, segments, counts, region_router{regions}, segment_capacity, counter, engine,
+              action, route_spill{});
             routed = true;
           }
         }
@@ -1088,7 +1249,7 @@ class table_engine {
     }
     // ---- pass 2 ----
     this->probe_segments<Counted>(
-      segments, counts, num_regions, 1u, segment_capacity, counter, engine, action, stream);
+      segments, counts, num_regions, 1u, segment_capacity, counter, engine, action, stream, first_slot, slice_slots);
     this->scratch_free(base, stream.get());
     return true;
   }
@@ -1104,16 +1265,23 @@ class table_engine {
                       size_type* counter,
                       EngineT const& engine,
                       Action action,
-                      cuda::stream_ref stream)
+                      cuda::stream_ref stream,
+                      std::uint64_t first_slot  = 0,
+                      std::uint64_t slice_slots = 0,
+                      std::uint32_t region_begin = 0,
+                      std::uint32_t region_count = 0,
+                      bool source_major          = false)
   {
     using cuco::detail::index_type;
     auto const& t           = tuning();
-    auto const capacity     = static_cast<std::uint64_t>(storage_.capacity());
-    auto const table_bytes  = capacity * sizeof(value_type);
+    bool const partial      = region_count != 0 || source_major;
+    if (region_count == 0) { region_count = num_regions; }
+    auto const capacity     = slice_slots != 0 ? slice_slots : static_cast<std::uint64_t>(storage_.capacity());
+    auto const table_bytes  = static_cast<std::uint64_t>(storage_.capacity()) * sizeof(value_type);
     auto const region_slots = (capacity + num_regions - 1) / num_regions;
     constexpr int chunk     = EngineT::sector_chunk_slots;
 
-    if (t.blocked_stream_probe && segment_capacity % 16 == 0 &&
+    if (t.blocked_stream_probe && !partial && first_slot == 0 && slice_slots == 0 && segment_capacity % 16 == 0 &&
         (reinterpret_cast<std::uintptr_t>(segments) % 16) == 0) {
       auto run = [&](auto rows_tag, auto blocks_tag) {
         constexpr int Rows      = decltype(rows_tag)::value;
@@ -1175,8 +1343,12 @@ class table_engine {
         region_slots,
         table_bytes,
         t.blocked_prefetch ? static_cast<std::uint32_t>((share + 127) / 128 * 128) : 0u,
-        sources};
-      kernel<<<dim3{tiles_per_segment, num_regions * sources}, block_size, 0, stream.get()>>>(
+        sources,
+        first_slot,
+        region_begin,
+        num_regions,
+        source_major ? 1u : 0u};
+      kernel<<<dim3{tiles_per_segment, region_count * sources}, block_size, 0, stream.get()>>>(
         segments, layout, counter, engine, action);
     };
 #if defined(CUCO_B200_TUNABLE)
@@ -1243,7 +1415,8 @@ class table_engine {
                             std::uint32_t* spill_index,
                             unsigned int* spill_count,
                             Ref ref,
-                            cuda::stream_ref stream)
+                            cuda::stream_ref stream,
+                            bool staging = false)
   {
     using cuco::detail::index_type;
     auto in           = unwrap(first);
@@ -1251,18 +1424,63 @@ class table_engine {
     using engine_t    = std::decay_t<decltype(engine)>;
     using elem_type   = std::conditional_t<KeysOnly, key_type, value_type>;
     auto const capacity = static_cast<std::uint64_t>(storage_.capacity());
+    // staging: `segments.base[owner]` is the owner's block [region][cap] of a LOCAL buffer that the
+    // copy engines deliver later; otherwise it is the owner's own buffer, region-major, source-minor
     exchange_geometry const geometry{static_cast<std::uint32_t>(num_ranks),
                                      static_cast<std::uint32_t>(my_rank),
                                      plan.num_regions,
                                      plan.segment_capacity,
-                                     salt};
+                                     salt,
+                                     staging ? 1u : static_cast<std::uint32_t>(num_ranks),
+                                     staging ? 0u : static_cast<std::uint32_t>(my_rank)};
     auto const buckets = static_cast<std::size_t>(num_ranks) * plan.num_regions;
     CUCO_CUDA_TRY(cudaMemsetAsync(counts_local, 0, buckets * sizeof(unsigned int), stream.get()));
     CUCO_CUDA_TRY(cudaMemsetAsync(spill_count, 0, sizeof(unsigned int), stream.get()));
+    if constexpr (std::is_pointer_v<decltype(in)>) {
+      // staging a contiguous, 16-byte aligned array of slot images (mutations) or keys (lookups): the
+      // bulk-copy fed persistent router of the single-GPU blocked path, with (owner, bucket) buckets, a
+      // spill list and - for lookups - the staged position of every input element
+      using input_value = std::remove_cv_t<std::remove_pointer_t<decltype(in)>>;
+      if constexpr (std::is_same_v<input_value, elem_type> && sizeof(elem_type) >= 8) {
+        auto const& t = tuning();
+        if (staging && n > 0 && t.blocked_tile_route && (reinterpret_cast<std::uintptr_t>(in) % 16) == 0 &&
+            buckets <= 4096) {
+          using stencil_t   = thrust::constant_iterator<bool>;
+          auto const kernel = tile_route_kernel<tile_route_block_size,
+                                                engine_t::sector_chunk_slots,
+                                                false,
+                                                stencil_t,
+                                                always_true,
+                                                size_type,
+                                                engine_t,
+                                                action_insert,
+                                                exchange_router,
+                                                elem_type,
+                                                KeysOnly>;
+          auto const smem = tile_route_smem_bytes<tile_route_block_size, elem_type, KeysOnly>(
+            static_cast<std::uint32_t>(buckets));
+          if (opt_in_dynamic_smem(kernel, std::size_t{200} << 10) && smem <= (std::size_t{200} << 10)) {
+            auto const tiles =
+              cuco::detail::int_div_ceil(n, index_type{tile_route_block_size} * route_items_per_thread);
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile_route_block_size, smem);
+            auto const resident = std::max(1, per_sm) * cuco::detail::multiprocessor_count();
+            auto const grid     = static_cast<unsigned>(std::min<index_type>(tiles, resident));
+            exchange_router const router{region_map::over(capacity, plan.num_regions),
+                                         static_cast<std::uint32_t>(num_ranks),
+                                         salt};
+            kernel<<<grid, tile_route_block_size, smem, stream.get()>>>(
+              in, n, stencil_t{true}, always_true{}, static_cast<elem_type*>(segments.base[0]), counts_local, router,
+              plan.segment_capacity, static_cast<size_type*>(nullptr), engine, action_insert{},
+              route_spill{spill, spill_count, plan.spill_capacity, position_local, spill_index});
+            return;
+          }
+        }
+      }
+    }
     if (n > 0) {
-      unsigned __int128 const scaled = (static_cast<unsigned __int128>(plan.num_regions) << 64) / capacity;
-      region_map const regions{static_cast<std::uint64_t>(scaled) + 1, plan.num_regions};
-      auto const kernel = exchange_route_kernel<route_block_size, KeysOnly, decltype(in), engine_t>;
+      auto const regions = region_map::over(capacity, plan.num_regions);
+      auto const kernel  = exchange_route_kernel<route_block_size, KeysOnly, decltype(in), engine_t>;
       constexpr std::size_t smem = exchange_smem_bytes<route_block_size, elem_type, KeysOnly>();
       CUCO_EXPECTS(opt_in_dynamic_smem(kernel, smem),
                    "the device refused the dynamic shared memory the exchange router needs");
@@ -1281,9 +1499,82 @@ class table_engine {
                                                              geometry,
                                                              engine);
     }
+    if (staging) { return; }  // counts and spill flags travel with the staged segments
     auto const publish_grid = static_cast<unsigned>((buckets + 255) / 256);
     exchange_publish_kernel<<<publish_grid, 256, 0, stream.get()>>>(
       counts_local, spill_count, counts_recv, spill_flags, geometry);
+  }
+
+  /// Geometry of the staged exchange: every rank groups a batch of at most `n_max` elements by
+  /// (owner, table slice) - `groups` slices per shard - into a local buffer [owner][slice][cap].
+  [[nodiscard]] exchange_plan plan_stage(cuco::detail::index_type n_max, int num_ranks, int groups) const
+  {
+    CUCO_EXPECTS(num_ranks >= 1 && num_ranks <= exchange_max_ranks, "unsupported number of ranks");
+    CUCO_EXPECTS(groups >= 1 && groups * num_ranks <= route_max_regions, "too many (owner, slice) buckets");
+    CUCO_EXPECTS(n_max >= 0 && n_max < (cuco::detail::index_type{1} << 32),
+                 "exchange batches are limited to 2^32 - 1 elements per rank");
+    auto const segments = static_cast<std::uint64_t>(groups) * static_cast<std::uint64_t>(num_ranks);
+    auto const mean     = (static_cast<std::uint64_t>(n_max) + segments - 1) / segments;
+    // owner and slice are both hash-uniform: 1/32 of slack is > 20 sigma from 2^17 elements per bucket up
+    return exchange_plan{static_cast<std::uint32_t>(groups),
+                         static_cast<std::uint32_t>((mean + mean / 32 + 1024 + 15) / 16 * 16),
+                         static_cast<std::uint32_t>(
+                           std::max<std::uint64_t>(65536, static_cast<std::uint64_t>(n_max) / 8))};
+  }
+
+  /// The slots [first, first + count) of table slice `group` of `groups` (same map on every rank).
+  [[nodiscard]] std::pair<std::uint64_t, std::uint64_t> slice_of(std::uint32_t group, std::uint32_t groups) const noexcept
+  {
+    auto const capacity = static_cast<std::uint64_t>(storage_.capacity());
+    auto const map      = region_map::over(capacity, groups);
+    auto const first    = map.region_begin(group);
+    auto const last     = group + 1 == groups ? capacity : map.region_begin(group + 1);
+    return {first, last - first};
+  }
+
+  /// Owner side of the staged exchange: applies the `num_ranks` received segments of ONE table slice
+  /// (contiguous [source][cap], fill counts in `counts_recv[source]`) - an ordinary gappy batch whose
+  /// keys all hash into that slice, so the L2-blocked path divides just the slice into regions.
+  template <typename Ref, typename Action>
+  void exchange_apply_async(value_type const* segments,
+                            unsigned int const* counts_recv,
+                            std::uint32_t segment_capacity,
+                            int num_ranks,
+                            std::uint32_t group,
+                            std::uint32_t groups,
+                            Ref ref,
+                            Action action,
+                            cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    if constexpr (!(engine_t::single_cas && engine_t::pow2_slot)) {
+      CUCO_FAIL("the exchange path needs slots that one CAS can claim (4, 8 or packed 16 bytes)");
+    } else {
+      CUCO_EXPECTS(this->fast_path_ok(true), "the exchange path needs container-owned storage without tombstones");
+      auto const virtual_n     = index_type{segment_capacity} * num_ranks;
+      auto const live          = segment_live{counts_recv, segment_capacity};
+      auto const [first, span] = this->slice_of(group, groups);
+      auto const slice_bytes   = span * sizeof(value_type);
+      auto const& t            = tuning();
+      auto const in            = segments;
+      auto const index         = thrust::counting_iterator<index_type>{0};
+      if constexpr (Action::blockable) {
+        // same rule as blocking_pays(), applied to the slice the batch is confined to
+        bool const dense = static_cast<std::uint64_t>(virtual_n) * 64 >= slice_bytes;
+        bool const pays  = t.blocked > 0 || (t.blocked < 0 && slice_bytes >= (std::size_t{2} * t.region_bytes) &&
+                                             virtual_n >= (index_type{1} << 16) && dense);
+        if (pays && slice_bytes / route_max_regions <= (std::size_t{64} << 20)) {
+          if (this->template blocked_mutate<false>(in, virtual_n, index, live, static_cast<size_type*>(nullptr),
+                                                   engine, action, stream, first, span)) {
+            return;
+          }
+        }
+      }
+      this->template direct_mutate<false>(in, virtual_n, index, live, static_cast<size_type*>(nullptr), engine,
+                                          action, stream);
+    }
   }
 
   /// Owner side of a routed mutation: probes the received segments region by region.
@@ -1329,6 +1620,93 @@ class table_engine {
     }
   }
 
+  /// Owner side of the staged exchange, fine mode: the sources already grouped their batches by the
+  /// L2 regions of this shard (`num_regions` of them), segments arrive source-major
+  /// [source][region][cap]; probes regions [region_begin, region_begin + region_count) with the
+  /// region's slots resident in L2 - no local regrouping pass.
+  template <typename Ref, typename Action>
+  void exchange_probe_async(value_type const* segments,
+                            unsigned int const* counts_recv,
+                            std::uint32_t num_regions,
+                            std::uint32_t segment_capacity,
+                            int num_ranks,
+                            std::uint32_t region_begin,
+                            std::uint32_t region_count,
+                            Ref ref,
+                            Action action,
+                            cuda::stream_ref stream)
+  {
+    auto const engine = ref.engine();
+    using engine_t    = std::decay_t<decltype(engine)>;
+    if constexpr (!(engine_t::single_cas && engine_t::pow2_slot && Action::blockable)) {
+      CUCO_FAIL("the exchange path needs slots that one CAS can claim (4, 8 or packed 16 bytes)");
+    } else {
+      CUCO_EXPECTS(this->fast_path_ok(true), "the exchange path needs container-owned storage without tombstones");
+      CUCO_EXPECTS(region_begin + region_count <= num_regions && region_count > 0, "region range out of bounds");
+      this->template probe_segments<false>(segments,
+                                           counts_recv,
+                                           num_regions,
+                                           static_cast<std::uint32_t>(num_ranks),
+                                           segment_capacity,
+                                           static_cast<size_type*>(nullptr),
+                                           engine,
+                                           action,
+                                           stream,
+                                           0,
+                                           0,
+                                           region_begin,
+                                           region_count,
+                                           true);
+    }
+  }
+
+  /// Owner side of a staged lookup: the received keys [source][cap] (fill counts per source) are an
+  /// ordinary gappy batch for the single-GPU lookup kernel, answered in arrival order into a local
+  /// buffer of the same shape (the copy engines return it to the sources).
+  template <typename Result, typename Ref, typename Emit>
+  void exchange_lookup_local_async(key_type const* segments,
+                                   unsigned int const* counts_recv,
+                                   Result* results,
+                                   std::uint32_t segment_capacity,
+                                   int num_ranks,
+                                   Ref ref,
+                                   Emit emit,
+                                   cuda::stream_ref stream)
+  {
+    using cuco::detail::index_type;
+    this->lookup(segments,
+                 index_type{segment_capacity} * num_ranks,
+                 thrust::counting_iterator<index_type>{0},
+                 segment_live{counts_recv, segment_capacity},
+                 results,
+                 ref,
+                 emit,
+                 stream);
+  }
+
+  /// L2 regions a shard is divided into for the fine mode of the staged exchange (the same rule as the
+  /// single-GPU blocked path), or 0 when `num_ranks` x regions would exceed the router's bucket limit.
+  [[nodiscard]] std::uint32_t exchange_fine_regions(int num_ranks) const noexcept
+  {
+    auto const& t          = tuning();
+    auto const table_bytes = static_cast<std::uint64_t>(storage_.capacity()) * sizeof(value_type);
+    // Budget of (owner, region) buckets for the source's router. Measured on B200 (tools/stage_probe.py,
+    // profiles/r02_stage_probe.jsonl, 100 M pairs): 0.75 - 0.79 ms up to ~200 buckets, 1.32 ms at 400,
+    // 2.2 ms at 800 - a tile of 2048 elements then holds 2 - 3 per bucket and the copy-out degenerates to
+    // one 16-byte store per sector. Beyond the budget the coarse mode (source groups by owner and slice,
+    // 0.76 ms; the owner regroups, 0.75 ms) is cheaper.
+    std::uint64_t budget = 256;
+    if (char const* s = std::getenv("CUCO_B200_FINE_BUCKETS")) { budget = static_cast<std::uint64_t>(std::max(1, std::atoi(s))); }
+    std::uint64_t const limit =
+      std::min<std::uint64_t>(route_max_regions, budget) / static_cast<std::uint64_t>(num_ranks);
+    // 16 MiB regions when they fit the bucket budget, else up to 64 MiB ones (0.8x the probe rate)
+    for (std::uint64_t bytes = t.region_bytes; bytes <= (std::uint64_t{64} << 20); bytes *= 2) {
+      auto const regions = std::max<std::uint64_t>(2, (table_bytes + bytes - 1) / bytes);
+      if (regions <= limit) { return static_cast<std::uint32_t>(regions); }
+    }
+    return 0;
+  }
+
   /// Owner side of a routed lookup: results go straight into the sources' result buffers.
   template <typename Result, typename Ref, typename Emit>
   void exchange_lookup_async(key_type const* segments,
@@ -1339,18 +1717,23 @@ class table_engine {
                              int my_rank,
                              Ref ref,
                              Emit emit,
-                             cuda::stream_ref stream) const
+                             cuda::stream_ref stream,
+                             bool local_results = false) const
   {
     using cuco::detail::index_type;
     auto const engine = ref.engine();
     using engine_t    = std::decay_t<decltype(engine)>;
     CUCO_EXPECTS(this->fast_path_ok(false), "the exchange path needs container-owned storage");
     constexpr int chunk = engine_t::sector_chunk_slots;
+    // local_results: `results.base[source]` is that source's block of a LOCAL buffer (the copy
+    // engines return it); otherwise the source's own buffer, written through peer stores
     exchange_geometry const geometry{static_cast<std::uint32_t>(num_ranks),
                                      static_cast<std::uint32_t>(my_rank),
                                      plan.num_regions,
                                      plan.segment_capacity,
-                                     0};
+                                     0,
+                                     static_cast<std::uint32_t>(num_ranks),
+                                     local_results ? 0u : static_cast<std::uint32_t>(my_rank)};
     auto run = [&](auto kpt_tag) {
       constexpr int kpt            = decltype(kpt_tag)::value;
       auto const tiles_per_segment = static_cast<unsigned>(
@@ -1450,7 +1833,6 @@ class table_engine {
   /// different streams never share scratch state (the reference allocates a counter per call too,
   /// impl.cuh:337-347); the pool keeps freed memory (release threshold = max), so a steady stream of
   /// calls costs no cudaMalloc after the first.
-  mutable cudaMemPool_t pool_{nullptr};
 };
 
 }  // namespace cuco::b200

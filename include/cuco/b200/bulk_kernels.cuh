@@ -621,17 +621,34 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void generic_mutate_kernel(InputIt firs
 
 /// Maps a home slot to its region: floor(slot * num_regions / capacity) by multiply-high.
 struct region_map {
-  std::uint64_t scale;  ///< ceil(2^64 * num_regions / capacity) clamped so the result < num_regions
+  std::uint64_t scale;  ///< ceil(2^64 * num_regions / slots) clamped so the result < num_regions
   std::uint32_t num_regions;
+  std::uint64_t first_slot = 0;  ///< the regions divide the slice [first_slot, first_slot + slots) of the
+                                 ///< table (the whole table unless the batch is known to be confined)
 
   __host__ __device__ std::uint32_t operator()(std::uint64_t slot) const noexcept
   {
+    slot -= first_slot;  // a slot in front of the slice wraps to a huge value and lands in the last region
 #if defined(__CUDA_ARCH__)
     auto const r = static_cast<std::uint32_t>(__umul64hi(slot, scale));
 #else
     auto const r = static_cast<std::uint32_t>((static_cast<unsigned __int128>(slot) * scale) >> 64);
 #endif
     return r < num_regions ? r : num_regions - 1;
+  }
+
+  /// First slot of region `r` (host side: exact inverse of operator()).
+  [[nodiscard]] std::uint64_t region_begin(std::uint32_t r) const noexcept
+  {
+    unsigned __int128 const numerator = static_cast<unsigned __int128>(r) << 64;
+    return first_slot + static_cast<std::uint64_t>((numerator + scale - 1) / scale);
+  }
+
+  /// Map of `num_regions` regions over `slots` slots starting at `first_slot`.
+  [[nodiscard]] static region_map over(std::uint64_t slots, std::uint32_t num_regions, std::uint64_t first_slot = 0) noexcept
+  {
+    unsigned __int128 const scaled = (static_cast<unsigned __int128>(num_regions) << 64) / (slots ? slots : 1);
+    return region_map{static_cast<std::uint64_t>(scaled) + 1, num_regions, first_slot};
   }
 };
 
@@ -799,6 +816,11 @@ struct blocked_layout {
   std::uint64_t table_bytes;        ///< end of the slot array (prefetch clamp)
   std::uint32_t prefetch_bytes;     ///< per-CTA share of the next region (multiple of 128), 0 = off
   std::uint32_t sources;            ///< segments per region (1; number of ranks for exchanged batches)
+  std::uint64_t first_slot = 0;     ///< region 0 starts at this slot (batches confined to a table slice)
+  std::uint32_t region_begin  = 0;  ///< this launch covers regions [region_begin, region_begin + gridDim.y / sources)
+  std::uint32_t total_regions = 0;  ///< regions the table (slice) is divided into; 0 = those of this launch
+  std::uint32_t source_major  = 0;  ///< 0: segment (region, source) is number region * sources + source;
+                                    ///< 1: source * total_regions + region (exchange buffers filled per source)
 };
 
 template <int BlockSize,
@@ -817,18 +839,22 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void blocked_mutate_kernel(
   Action action)
 {
   constexpr index_type tile = index_type{BlockSize} * KeysPerThread;
-  // segment = region * sources + source: CTAs are dispatched region by region
-  std::uint32_t const segment     = blockIdx.y;
-  std::uint32_t const region      = segment / layout.sources;
-  std::uint32_t const num_regions = gridDim.y / layout.sources;
+  // blockIdx.y = region * sources + source: CTAs are dispatched region by region
+  std::uint32_t const local_region = blockIdx.y / layout.sources;
+  std::uint32_t const source       = blockIdx.y - local_region * layout.sources;
+  std::uint32_t const region       = layout.region_begin + local_region;
+  std::uint32_t const num_regions  = layout.total_regions != 0 ? layout.total_regions : gridDim.y / layout.sources;
+  std::uint32_t const segment =
+    layout.source_major != 0 ? source * num_regions + region : region * layout.sources + source;
 
   if (layout.prefetch_bytes != 0 && threadIdx.x == 0 && region + 1 < num_regions) {
     // stream this CTA's share of the next region's slots into L2 while this region is probed
-    std::uint64_t const share_index =
-      std::uint64_t{segment - region * layout.sources} * gridDim.x + blockIdx.x;
-    std::uint64_t const begin = (std::uint64_t{region} + 1) * layout.region_slots * Engine::slot_bytes +
-                                share_index * layout.prefetch_bytes;
-    std::uint64_t const limit = (std::uint64_t{region} + 2) * layout.region_slots * Engine::slot_bytes;
+    std::uint64_t const share_index = std::uint64_t{source} * gridDim.x + blockIdx.x;
+    std::uint64_t const begin =
+      (layout.first_slot + (std::uint64_t{region} + 1) * layout.region_slots) * Engine::slot_bytes +
+      share_index * layout.prefetch_bytes;
+    std::uint64_t const limit =
+      (layout.first_slot + (std::uint64_t{region} + 2) * layout.region_slots) * Engine::slot_bytes;
     std::uint64_t end = begin + layout.prefetch_bytes;
     if (end > limit) { end = limit; }
     if (end > (layout.table_bytes & ~std::uint64_t{15})) { end = layout.table_bytes & ~std::uint64_t{15}; }
@@ -1102,6 +1128,11 @@ struct exchange_geometry {
   std::uint32_t num_regions;       ///< R (P * R <= route_max_regions)
   std::uint32_t segment_capacity;  ///< cap
   std::uint64_t salt;
+  /// Where a routed element lands behind `base[owner]`: segment (region * dest_stride + dest_slot).
+  /// Peer stores into the owners' buffers use (P, my_rank): the owner sees its segments region-major,
+  /// source-minor. Staging into a LOCAL buffer (copied to the owners later) uses (1, 0).
+  std::uint32_t dest_stride;
+  std::uint32_t dest_slot;
 };
 
 template <typename Key>
@@ -1199,9 +1230,27 @@ CUCO_KERNEL __launch_bounds__(BlockSize, 2) void exchange_route_kernel(
         bucket[j]         = owner * R + region;
       }
     }
+    if (num_buckets <= 8) {
+      // Few buckets (routing by owner, or by owner and a handful of table slices): one shared-memory
+      // atomic per element would serialise the whole tile on a few counters. The lanes of a warp that
+      // share a bucket elect a leader, which reserves their ranks with ONE atomic.
+      unsigned const lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int j = 0; j < items; ++j) {
-      if (bucket[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[bucket[j]], 1u); }
+      for (int j = 0; j < items; ++j) {
+        unsigned const same   = __match_any_sync(0xffffffffu, bucket[j]);
+        unsigned const leader = static_cast<unsigned>(__ffs(same)) - 1u;
+        unsigned int base     = 0;
+        if (lane == leader && bucket[j] != 0xffffffffu) {
+          base = atomicAdd(&tile_hist[bucket[j]], static_cast<unsigned int>(__popc(same)));
+        }
+        base    = __shfl_sync(0xffffffffu, base, static_cast<int>(leader));
+        rank[j] = base + static_cast<unsigned int>(__popc(same & ((1u << lane) - 1u)));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < items; ++j) {
+        if (bucket[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[bucket[j]], 1u); }
+      }
     }
     __syncthreads();
     {
@@ -1261,7 +1310,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize, 2) void exchange_route_kernel(
         std::uint32_t const region = b - owner * R;
         auto* const segment =
           static_cast<elem_type*>(peers.base[owner]) +
-          (std::uint64_t{region} * P + geometry.my_rank) * cap;
+          (std::uint64_t{region} * geometry.dest_stride + geometry.dest_slot) * cap;
         segment[where] = stage[pos];
         // the tile's 4096 positions are written together, so these scattered 4-byte stores merge
         // into full lines in L2; the return trip then GATHERS by position with coalesced output
@@ -1294,7 +1343,7 @@ CUCO_KERNEL void exchange_publish_kernel(unsigned int const* counts_local,
   for (std::uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < P * R; b += gridDim.x * blockDim.x) {
     std::uint32_t const owner = b / R, region = b - owner * R;
     unsigned int const filled = counts_local[b];
-    static_cast<unsigned int*>(counts_recv.base[owner])[region * P + geometry.my_rank] =
+    static_cast<unsigned int*>(counts_recv.base[owner])[region * geometry.dest_stride + geometry.dest_slot] =
       filled < geometry.segment_capacity ? filled : geometry.segment_capacity;
   }
   if (blockIdx.x == 0 && threadIdx.x < P) {
@@ -1303,12 +1352,17 @@ CUCO_KERNEL void exchange_publish_kernel(unsigned int const* counts_local,
 }
 
 /// Owner side of a routed lookup: probes the keys of segment g = region * P + source and stores the
-/// results straight into the source's result buffer (peer store) at the key's source-side position.
+/// results at the key's position behind `results.base[source]`, segment
+/// (geometry.dest_slot * R + region): the SOURCE's result buffer (peer stores, dest_slot = this rank)
+/// or a local buffer that the copy engines return afterwards (dest_slot = 0, one base per source).
+/// Every result is kept in a register until its key is resolved and stored by ONE instruction per
+/// key slot, so a warp writes whole 256-byte runs (8-byte results) instead of the hit / miss /
+/// leftover fragments of the probe loop - that matters for stores that cross NVLink.
 template <int BlockSize, int KeysPerThread, int ChunkSlots, typename Result, typename Engine, typename Emit>
 CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
   typename Engine::key_type const* segments,
   unsigned int const* counts_recv,
-  exchange_peers results,  ///< sources' result buffers, source-side layout
+  exchange_peers results,
   exchange_geometry geometry,
   Engine engine,
   Emit emit)
@@ -1326,26 +1380,30 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
   std::uint32_t const source =
     (blockIdx.y - region * geometry.num_ranks + geometry.my_rank + 1) % geometry.num_ranks;
   std::uint32_t const segment = region * geometry.num_ranks + source;
-  index_type const count      = counts_recv[segment];
-  index_type const tile_base  = index_type{blockIdx.x} * tile;
+  auto const stored           = counts_recv[segment];
+  index_type const count =
+    stored < geometry.segment_capacity ? index_type{stored} : index_type{geometry.segment_capacity};
+  index_type const tile_base = index_type{blockIdx.x} * tile;
   if (tile_base >= count) { return; }
 
   key_type const* const in = segments + std::uint64_t{segment} * geometry.segment_capacity;
   Result* const out        = static_cast<Result*>(results.base[source]) +
-                      (std::uint64_t{geometry.my_rank} * geometry.num_regions + region) *
+                      (std::uint64_t{geometry.dest_slot} * geometry.num_regions + region) *
                         geometry.segment_capacity;
 
   uninitialized<key_type> key[KeysPerThread];
   cursor cur[KeysPerThread];
-  unsigned pending = 0;
+  Result answer[KeysPerThread];
+  unsigned live = 0;
 #pragma unroll
   for (int j = 0; j < KeysPerThread; ++j) {
     index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
     if (idx < count) {
       key[j].value = read_input(in, idx);
-      pending |= 1u << j;
+      live |= 1u << j;
     }
   }
+  unsigned pending = live;
 #pragma unroll
   for (int j = 0; j < KeysPerThread; ++j) {
     if (pending & (1u << j)) { cur[j] = engine.make_cursor(key[j].value); }
@@ -1360,7 +1418,6 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
 #pragma unroll
     for (int j = 0; j < KeysPerThread; ++j) {
       if (pending & (1u << j)) {
-        index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
         int const begin_off =
           static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
         int const valid = engine.template chunk_valid<ChunkSlots>(cur[j]);
@@ -1371,11 +1428,11 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
             auto const slot  = chunk_slot<slot_type>(raw[j], i);
             auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
             if (state == equal_result::EQUAL) {
-              out[idx] = static_cast<Result>(emit.hit(slot));
-              done     = true;
+              answer[j] = static_cast<Result>(emit.hit(slot));
+              done      = true;
             } else if (state == equal_result::EMPTY) {
-              out[idx] = static_cast<Result>(emit.miss());
-              done     = true;
+              answer[j] = static_cast<Result>(emit.miss());
+              done      = true;
             }
           }
         }
@@ -1400,27 +1457,31 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
           c = cur[j];
         }
       }
-      index_type const idx = tile_base + index_type{jj} * BlockSize + threadIdx.x;
-      auto const raw       = engine.template load_chunk<ChunkSlots, policy>(c);
-      int const begin_off  = static_cast<int>(c.slot - Engine::template chunk_begin<ChunkSlots>(c));
-      int const valid      = engine.template chunk_valid<ChunkSlots>(c);
-      bool done            = false;
+      auto const raw      = engine.template load_chunk<ChunkSlots, policy>(c);
+      int const begin_off = static_cast<int>(c.slot - Engine::template chunk_begin<ChunkSlots>(c));
+      int const valid     = engine.template chunk_valid<ChunkSlots>(c);
+      bool done           = false;
+      Result found{};
 #pragma unroll
       for (int i = 0; i < ChunkSlots; ++i) {
         if (!done && i >= begin_off && i < begin_off + valid) {
           auto const slot  = chunk_slot<slot_type>(raw, i);
           auto const state = engine.classify_lookup(k, Engine::key_of(slot));
           if (state == equal_result::EQUAL) {
-            out[idx] = static_cast<Result>(emit.hit(slot));
-            done     = true;
+            found = static_cast<Result>(emit.hit(slot));
+            done  = true;
           } else if (state == equal_result::EMPTY) {
-            out[idx] = static_cast<Result>(emit.miss());
-            done     = true;
+            found = static_cast<Result>(emit.miss());
+            done  = true;
           }
         }
       }
       if (done) {
         pending &= ~(1u << jj);
+#pragma unroll
+        for (int j = 0; j < KeysPerThread; ++j) {
+          if (j == jj) { answer[j] = found; }
+        }
       } else {
         engine.advance(c, valid);
 #pragma unroll
@@ -1429,6 +1490,11 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void exchange_lookup_kernel(
         }
       }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < KeysPerThread; ++j) {
+    index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+    if (live & (1u << j)) { out[idx] = answer[j]; }
   }
 }
 
@@ -1463,16 +1529,70 @@ CUCO_KERNEL __launch_bounds__(256) void exchange_unpermute_kernel(Result const* 
 }
 
 // =================================================================================================
-// erase (tombstoning) - one key per thread
+// erase (tombstoning) - two keys per thread
 // =================================================================================================
 /// `ChunkSlots` > window size only on container-owned (padded, 32-byte aligned) storage: the walk
 /// then reads the whole sector a probe lands in, like the lookup kernels.
 template <int BlockSize, int ChunkSlots, typename InputIt, typename Engine>
 CUCO_KERNEL __launch_bounds__(BlockSize) void erase_kernel(InputIt first, index_type n, Engine engine)
 {
-  for (index_type idx = cuco::detail::global_thread_id(); idx < n;
-       idx += cuco::detail::grid_stride()) {
-    engine.template scalar_erase<ChunkSlots, load_policy::streaming>(read_input(first, idx));
+  // Two keys per thread, both input loads and both home-chunk loads posted before either is consumed
+  // (one key per thread leaves the DRAM round trips of a thread back to back: 15.6 G keys/s, the same as
+  // cuco's one-key-per-thread kernel). A key whose home chunk does not settle it continues with the
+  // general walk.
+  using slot_type  = typename Engine::value_type;
+  using cursor     = typename Engine::cursor;
+  using probe_type = decltype(read_input(first, index_type{0}));
+  constexpr int keys_per_thread = 2;
+  constexpr index_type tile     = index_type{BlockSize} * keys_per_thread;
+  constexpr auto policy         = load_policy::streaming;
+
+  for (index_type tile_base = index_type{blockIdx.x} * tile; tile_base < n;
+       tile_base += index_type{gridDim.x} * tile) {
+    uninitialized<probe_type> key[keys_per_thread];
+    cursor cur[keys_per_thread];
+    unsigned pending = 0;
+#pragma unroll
+    for (int j = 0; j < keys_per_thread; ++j) {
+      index_type const idx = tile_base + index_type{j} * BlockSize + threadIdx.x;
+      if (idx < n) {
+        key[j].value = read_input(first, idx);
+        pending |= 1u << j;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < keys_per_thread; ++j) {
+      if (pending & (1u << j)) { cur[j] = engine.make_cursor(key[j].value); }
+    }
+    raw_chunk<ChunkSlots * Engine::slot_bytes> raw[keys_per_thread];
+#pragma unroll
+    for (int j = 0; j < keys_per_thread; ++j) {
+      if (pending & (1u << j)) { raw[j] = engine.template load_chunk<ChunkSlots, policy>(cur[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < keys_per_thread; ++j) {
+      if (!(pending & (1u << j))) { continue; }
+      int const begin_off = static_cast<int>(cur[j].slot - Engine::template chunk_begin<ChunkSlots>(cur[j]));
+      int const valid     = engine.template chunk_valid<ChunkSlots>(cur[j]);
+      bool done           = false;
+#pragma unroll
+      for (int i = 0; i < ChunkSlots; ++i) {
+        if (!done && i >= begin_off && i < begin_off + valid) {
+          auto const slot  = chunk_slot<slot_type>(raw[j], i);
+          auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
+          if (state == equal_result::EQUAL) {
+            engine.retire_slot(engine.slots() + (cur[j].slot + (i - begin_off)), Engine::key_of(slot));
+            done = true;
+          } else if (state == equal_result::EMPTY) {
+            done = true;
+          }
+        }
+      }
+      if (!done) {
+        engine.advance(cur[j], valid);
+        engine.template erase_from<ChunkSlots, policy>(cur[j], key[j].value);
+      }
+    }
   }
 }
 

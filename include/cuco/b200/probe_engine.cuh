@@ -637,8 +637,13 @@ class probe_engine {
       value_type* cand    = nullptr;
       value_type cand_img = empty_slot_;
 
+      size_type ordinal = 0;  // slots of the probe sequence examined before the current one
       walk<ChunkSlots, Policy>(start, [&](size_type index, value_type slot) {
         auto const state = classify_insert(key, key_of(slot));
+        struct count_on_exit {
+          size_type& n;
+          __device__ ~count_on_exit() { ++n; }
+        } const counted{ordinal};
         if (tombstone) { ++seen; }
         if constexpr (!allows_duplicates) {
           if (state == equal_result::EQUAL) {
@@ -648,6 +653,30 @@ class probe_engine {
         }
         if (state != equal_result::AVAILABLE) { return false; }
 
+        if constexpr (!allows_duplicates && cg_size > 1) {
+          // Reference rule for a cg_size-wide probe step (ref_impl.cuh:433-458): every lane reports the
+          // first slot of ITS window that is available or equal, and an EQUAL report from any lane of
+          // the step outranks an AVAILABLE one from a lower lane. Only an erased slot can precede the
+          // key inside one step (an empty one would have taken the key when it was inserted), so the
+          // rest of the step is examined only then.
+          if (has_tombstones() && !is_empty_key(key_of(slot))) {
+            constexpr int group_slots = cg_size * window_size;
+            int const pos             = static_cast<int>(ordinal % group_slots);
+            auto const cap            = static_cast<size_type>(storage_.capacity());
+            for (int p = (pos / window_size + 1) * window_size; p < group_slots;) {
+              size_type at = index + static_cast<size_type>(p - pos);
+              if (at >= cap) { at -= cap; }
+              key_type later_key;  // the key leads the slot image (pair.first, or the slot itself)
+              memcpy(&later_key, table + at, sizeof(key_type));
+              auto const later = classify_insert(key, later_key);
+              if (later == equal_result::EQUAL) {
+                found = table + at;
+                return true;
+              }
+              p = (later == equal_result::AVAILABLE) ? (p / window_size + 1) * window_size : p + 1;
+            }
+          }
+        }
         bool truly_empty = !tombstone || is_empty_key(key_of(slot));
         if (tombstone && !truly_empty && cand != nullptr && seen > static_cast<size_type>(capacity())) {
           truly_empty = true;  // one full cycle without an empty slot: settle for the remembered tombstone
@@ -782,8 +811,15 @@ class probe_engine {
             typename ProbeKey>
   __device__ bool scalar_erase(ProbeKey const& key) noexcept
   {
+    return this->template erase_from<ChunkSlots, Policy>(make_cursor(key), key);
+  }
+
+  /// `scalar_erase` resumed at `start` (a cursor further down the key's probe sequence).
+  template <int ChunkSlots, load_policy Policy, typename ProbeKey>
+  __device__ bool erase_from(cursor start, ProbeKey const& key) noexcept
+  {
     bool erased = false;
-    walk<ChunkSlots, Policy>(make_cursor(key), [&](size_type index, value_type slot) {
+    walk<ChunkSlots, Policy>(start, [&](size_type index, value_type slot) {
       auto const state = classify_lookup(key, key_of(slot));
       if (state == equal_result::EMPTY) { return true; }
       if (state != equal_result::EQUAL) { return false; }
@@ -1079,7 +1115,7 @@ class probe_engine {
     return insert_result::CONTINUE;
   }
 
- private:
+ public:
   /// key -> erased sentinel (payload reset to the empty payload); true iff we made the transition.
   __device__ bool retire_slot(value_type* address, key_type observed_key) noexcept
   {
@@ -1106,6 +1142,8 @@ class probe_engine {
         observed_key, erased_key_, cuda::memory_order_relaxed);
     }
   }
+
+ private:
 
   /// Chunks wider than one slot need the vector path; single odd-sized slots use a plain copy.
   template <int ChunkSlots, load_policy Policy>

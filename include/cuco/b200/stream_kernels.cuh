@@ -153,13 +153,78 @@ constexpr int tile_route_block_size = 256;  ///< tile = 2048 elements: three CTA
 
 /// Dynamic shared memory of `tile_route_kernel`: two element tiles, the bucket of every staged
 /// position, three bucket arrays.
-template <int BlockSize, typename Slot>
+template <int BlockSize, typename Slot, bool WithIndex = false>
 constexpr std::size_t tile_route_smem_bytes(std::uint32_t num_buckets) noexcept
 {
   std::size_t const tile = std::size_t{BlockSize} * route_items_per_thread;
-  return 2 * tile * sizeof(Slot) + tile * sizeof(std::uint16_t) +
+  return 2 * tile * sizeof(Slot) + tile * sizeof(std::uint16_t) + (WithIndex ? tile * sizeof(std::uint32_t) : 0) +
          3 * std::size_t{num_buckets} * sizeof(unsigned int);
 }
+
+/// Bucket of a key for the single-GPU blocked path: the L2 region of its home slot.
+struct region_router {
+  region_map regions;
+  static constexpr bool spills = false;  ///< a full segment is finished on the spot (local table)
+
+  [[nodiscard]] __host__ __device__ std::uint32_t num_buckets() const noexcept { return regions.num_regions; }
+
+  template <typename Engine, typename Key>
+  [[nodiscard]] __device__ std::uint32_t operator()(Engine const& engine, Key const& key) const noexcept
+  {
+    return regions(engine.make_cursor(key).slot);
+  }
+};
+
+/// Bucket of a key for the staged multi-GPU exchange: (owner rank, region of the OWNER's shard) -
+/// every shard has the same geometry, so the source can compute both.
+struct exchange_router {
+  region_map regions;
+  std::uint32_t num_ranks;
+  std::uint64_t salt;
+  static constexpr bool spills = true;  ///< a full segment overflows into the spill list (foreign table)
+
+  [[nodiscard]] __host__ __device__ std::uint32_t num_buckets() const noexcept
+  {
+    return num_ranks * regions.num_regions;
+  }
+
+  template <typename Engine, typename Key>
+  [[nodiscard]] __device__ std::uint32_t operator()(Engine const& engine, Key const& key) const noexcept
+  {
+    auto const owner = exchange_owner(exchange_key_bits(key), salt, num_ranks);
+    if (regions.num_regions == 1) { return owner; }  // routing by owner only: no need for the table hash
+    return owner * regions.num_regions + regions(engine.make_cursor(key).slot);
+  }
+};
+
+/// `region_router` for batches whose overflow cannot be finished on the spot (probe keys of the
+/// blocked count / retrieve): elements of a full segment go to the spill list.
+struct region_spill_router : region_router {
+  static constexpr bool spills = true;
+};
+
+/// Key of a routed element: the element itself when probe keys are routed, else the slot image's key.
+template <typename Engine, typename Elem>
+[[nodiscard]] __device__ __forceinline__ auto const& routed_key(Elem const& element) noexcept
+{
+  if constexpr (cuda::std::is_same_v<Elem, typename Engine::value_type>) {
+    return Engine::key_of(element);
+  } else {
+    return element;
+  }
+}
+
+/// Where elements go whose segment is full (routers with `spills`).
+struct route_spill {
+  void* list                = nullptr;
+  unsigned int* count       = nullptr;
+  std::uint32_t capacity    = 0;
+  /// routers `WithIndex` (lookups: the answers must find their way back): position[i] = where input
+  /// element i was staged (bucket * segment_capacity + offset; 0xffffffff = spilled), and the input
+  /// index of every spilled element
+  std::uint32_t* position   = nullptr;
+  std::uint32_t* index      = nullptr;
+};
 
 /// `route_kernel` for a contiguous input range of slot images (`Slot const*`, 16-byte aligned):
 /// same ranking, staging and copy-out, but persistent, with the next tile loaded by the bulk-copy
@@ -172,29 +237,34 @@ template <int BlockSize,
           typename Predicate,
           typename Counter,
           typename Engine,
-          typename Action>
+          typename Action,
+          typename Router = region_router,
+          typename Elem   = typename Engine::value_type,
+          bool WithIndex  = false>
 CUCO_KERNEL __launch_bounds__(BlockSize) void tile_route_kernel(
-  typename Engine::value_type const* first,
+  Elem const* first,
   index_type n,
   StencilIt stencil,
   Predicate pred,
-  typename Engine::value_type* segments,
+  Elem* segments,
   unsigned int* region_counts,
-  region_map regions,
+  Router router,
   std::uint32_t segment_capacity,
   Counter* num_new,
   Engine engine,
-  Action action)
+  Action action,
+  route_spill spill = {})
 {
-  using slot_type           = typename Engine::value_type;
+  using slot_type           = Elem;  // routed element: a slot image, or a bare probe key
   constexpr int items       = route_items_per_thread;
   constexpr index_type tile = index_type{BlockSize} * items;
 
   extern __shared__ __align__(128) unsigned char route_dynamic_smem[];
-  std::uint32_t const num_regions = regions.num_regions;
+  std::uint32_t const num_regions = router.num_buckets();
   auto* const buffer0    = reinterpret_cast<slot_type*>(route_dynamic_smem);
   auto* const buffer1    = buffer0 + tile;
-  auto* const owner      = reinterpret_cast<std::uint16_t*>(buffer1 + tile);                  // [tile]
+  auto* const origin     = reinterpret_cast<std::uint32_t*>(buffer1 + tile);                  // [tile] (WithIndex)
+  auto* const owner      = reinterpret_cast<std::uint16_t*>(origin + (WithIndex ? tile : 0));  // [tile]
   auto* const tile_hist  = reinterpret_cast<unsigned int*>(owner + tile);                     // [R]
   auto* const tile_start = tile_hist + num_regions;                                           // [R]
   auto* const run_start  = tile_start + num_regions;                                          // [R]
@@ -259,14 +329,38 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void tile_route_kernel(
       if (idx < n) {
         unsigned const at = j * BlockSize + threadIdx.x;
         val[j].value      = at < in_buffer ? stage[at] : first[idx];
-        if (pred(*(stencil + idx))) {
-          region[j] = regions(engine.make_cursor(Engine::key_of(val[j].value)).slot);
+        bool keep;
+        if constexpr (cuda::std::is_same_v<StencilIt, slot_type const*>) {
+          // the batch is its own stencil (rehash: "insert the slots that are filled"): the element is
+          // already here, no second - dependent - load of the same 16 bytes
+          keep = (stencil == first) ? pred(val[j].value) : pred(*(stencil + idx));
+        } else {
+          keep = pred(*(stencil + idx));
         }
+        if (keep) { region[j] = router(engine, routed_key<Engine>(val[j].value)); }
       }
     }
+    if (num_regions <= 8) {
+      // few buckets (measured, profiles/r02_stage_probe.jsonl: the election wins up to ~8 buckets, plain
+      // shared-memory atomics from 16 up): the lanes of a warp that share a bucket reserve their ranks with ONE atomic
+      // (one atomic per element would serialise the tile on a handful of counters)
+      unsigned const lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int j = 0; j < items; ++j) {
-      if (region[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[region[j]], 1u); }
+      for (int j = 0; j < items; ++j) {
+        unsigned const same   = __match_any_sync(0xffffffffu, region[j]);
+        unsigned const leader = static_cast<unsigned>(__ffs(same)) - 1u;
+        unsigned int first_rank = 0;
+        if (lane == leader && region[j] != 0xffffffffu) {
+          first_rank = atomicAdd(&tile_hist[region[j]], static_cast<unsigned int>(__popc(same)));
+        }
+        first_rank = __shfl_sync(0xffffffffu, first_rank, static_cast<int>(leader));
+        rank[j]    = first_rank + static_cast<unsigned int>(__popc(same & ((1u << lane) - 1u)));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < items; ++j) {
+        if (region[j] != 0xffffffffu) { rank[j] = atomicAdd(&tile_hist[region[j]], 1u); }
+      }
     }
     __syncthreads();  // every element of the tile is in registers: the buffer may be overwritten
 
@@ -308,6 +402,9 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void tile_route_kernel(
         unsigned int const pos = tile_start[region[j]] + rank[j];
         stage[pos]             = val[j].value;
         owner[pos]             = static_cast<std::uint16_t>(region[j]);
+        if constexpr (WithIndex) {
+          origin[pos] = static_cast<std::uint32_t>(base + index_type{j} * BlockSize + threadIdx.x);
+        }
       }
     }
     __syncthreads();
@@ -318,7 +415,19 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void tile_route_kernel(
       std::uint64_t const where = std::uint64_t{run_start[r]} + (pos - tile_start[r]);
       if (where < segment_capacity) {
         segments[std::uint64_t{r} * segment_capacity + where] = stage[pos];
-      } else {
+        // the tile's positions are written together, so these scattered 4-byte stores merge in L2
+        if constexpr (WithIndex) {
+          spill.position[origin[pos]] = static_cast<std::uint32_t>(std::uint64_t{r} * segment_capacity + where);
+        }
+      } else if constexpr (Router::spills) {
+        // segment full (heavily skewed input): the caller finishes the spilled elements another way
+        unsigned int const at = atomicAdd(spill.count, 1u);
+        if (at < spill.capacity) {
+          static_cast<slot_type*>(spill.list)[at] = stage[pos];
+          if constexpr (WithIndex) { spill.index[at] = origin[pos]; }
+        }
+        if constexpr (WithIndex) { spill.position[origin[pos]] = 0xffffffffu; }
+      } else if constexpr (cuda::std::is_same_v<Elem, typename Engine::value_type>) {
         // segment full (heavily skewed input): finish this element now, unblocked
         mine += mutate_slow_path<ChunkSlots, load_policy::streaming>(engine, stage[pos], base + pos, action);
       }

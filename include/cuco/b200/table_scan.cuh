@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cuco/b200/bulk_kernels.cuh>
+#include <cuco/b200/match_kernels.cuh>
 #include <cuco/b200/probe_engine.cuh>
 #include <cuco/detail/error.hpp>
 #include <cuco/detail/utility/cuda.cuh>
@@ -34,35 +35,51 @@ struct filled_slot {
 };
 
 /// Appends every filled slot to the output through `write(position, slot)`.
+/// One tile = BlockSize x 4 slots: four independent slot loads per thread, per-thread fill count,
+/// CTA-wide exclusive scan, ONE atomic on the output cursor per tile (a warp-level ballot + atomic per
+/// 32 slots serialises 3 M atomics on one address for a 100 M-slot table: 4.7 ms against cuco's 3.7),
+/// then every thread writes its survivors at its own offset - the rows of a tile form one run.
 template <int BlockSize, typename Engine, typename Write>
 CUCO_KERNEL __launch_bounds__(BlockSize) void compact_kernel(Engine engine,
                                                              unsigned long long* cursor,
                                                              Write write)
 {
-  namespace cg        = cooperative_groups;
-  auto const* table   = engine.slots();
-  auto const n        = static_cast<index_type>(engine.capacity());
-  auto const filled   = filled_slot<Engine>{engine.empty_key_sentinel(), engine.erased_key_sentinel()};
-  auto const warp     = cg::tiled_partition<32>(cg::this_thread_block());
-  auto const rounds_n = ((n + 31) / 32) * 32;  // keep whole warps in the loop for the ballots
+  using slot_type      = typename Engine::value_type;
+  constexpr int items  = 4;
+  constexpr index_type tile = index_type{BlockSize} * items;
+  auto const* table    = engine.slots();
+  auto const n         = static_cast<index_type>(engine.capacity());
+  auto const filled    = filled_slot<Engine>{engine.empty_key_sentinel(), engine.erased_key_sentinel()};
+  __shared__ unsigned int warp_totals[BlockSize / 32];
+  __shared__ unsigned long long tile_base;
 
-  for (index_type i = cuco::detail::global_thread_id(); i < rounds_n;
-       i += cuco::detail::grid_stride()) {
-    bool keep = false;
-    typename Engine::value_type slot{};
-    if (i < n) {
-      slot = table[i];
-      keep = filled(slot);
+  for (index_type base = index_type{blockIdx.x} * tile; base < n; base += index_type{gridDim.x} * tile) {
+    slot_type slot[items];
+    unsigned keep = 0;
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const i = base + index_type{j} * BlockSize + threadIdx.x;
+      if (i < n) { slot[j] = load_streaming(table + i); }
     }
-    auto const votes = warp.ballot(keep);
-    if (votes == 0) { continue; }
-    unsigned long long base = 0;
-    if (warp.thread_rank() == 0) {
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      index_type const i = base + index_type{j} * BlockSize + threadIdx.x;
+      if (i < n && filled(slot[j])) { keep |= 1u << j; }
+    }
+    unsigned int offset, total;
+    block_exclusive_scan<BlockSize>(static_cast<unsigned int>(__popc(keep)), warp_totals, offset, total);
+    if (total == 0) { continue; }  // uniform across the CTA
+    if (threadIdx.x == 0) {
       cuda::atomic_ref<unsigned long long, cuda::thread_scope_device> ref{*cursor};
-      base = ref.fetch_add(__popc(votes), cuda::memory_order_relaxed);
+      tile_base = ref.fetch_add(total, cuda::memory_order_relaxed);
     }
-    base = warp.shfl(base, 0);
-    if (keep) { write(base + __popc(votes & ((1u << warp.thread_rank()) - 1)), slot); }
+    __syncthreads();
+    unsigned long long where = tile_base + offset;
+#pragma unroll
+    for (int j = 0; j < items; ++j) {
+      if (keep & (1u << j)) { write(where++, slot[j]); }
+    }
+    __syncthreads();  // tile_base is rewritten next round
   }
 }
 
@@ -71,20 +88,20 @@ inline unsigned long long compact_filled(Engine const& engine, Write write, cuda
 {
   constexpr int block = 256;
   unsigned long long* cursor{};
-  CUCO_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&cursor), sizeof(unsigned long long)));
+  CUCO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&cursor), sizeof(unsigned long long), stream.get()));
   CUCO_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream.get()));
   auto const n = static_cast<index_type>(engine.capacity());
   if (n > 0) {
     auto const kernel = compact_kernel<block, Engine, Write>;
     auto const grid =
-      persistent_grid(kernel, block, cuco::detail::int_div_ceil(n, index_type{block}));
+      persistent_grid(kernel, block, cuco::detail::int_div_ceil(n, index_type{block} * 4));
     kernel<<<grid, block, 0, stream.get()>>>(engine, cursor, write);
   }
   unsigned long long count = 0;
   CUCO_CUDA_TRY(
     cudaMemcpyAsync(&count, cursor, sizeof(count), cudaMemcpyDeviceToHost, stream.get()));
+  CUCO_CUDA_TRY(cudaFreeAsync(cursor, stream.get()));
   stream.wait();
-  CUCO_CUDA_TRY(cudaFree(cursor));
   return count;
 }
 

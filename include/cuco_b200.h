@@ -330,6 +330,97 @@ int cuco_b200_exchange_unpermute(cuco_b200_table* t,
                                  int what,
                                  void* stream);
 
+/* ---- staged exchange (no reference counterpart) -----------------------------------
+ * The transfer itself is left to the copy engines, so that it overlaps the owners' kernels:
+ *   1. exchange_stage   groups the local batch by (owner, table slice) into a LOCAL buffer
+ *                       stage[owner][slice][segment_capacity] (elements: slot images, or keys for
+ *                       lookups) and fills counts_local[owner * slices + slice]; position_local /
+ *                       spill* as for exchange_route. `slices` cuts every shard into equal slot ranges.
+ *   2. the caller copies block (owner, slice) of `stage` into the owner's receive buffer
+ *                       recv[slice][source][segment_capacity] and the matching fill counts into
+ *                       recv_counts[slice][source] (cudaMemcpyAsync over NVLink peer mappings; slice by
+ *                       slice, so that slice s + 1 travels while slice s is applied).
+ *   3. exchange_apply   (mutations) applies the num_ranks received segments of ONE slice - all their
+ *                       keys hash into that slice of the table, so the L2-blocked path regroups and
+ *                       probes just that slice. reduce_op as for exchange_mutate.
+ *      exchange_lookup_local (lookups) answers the received keys [source][segment_capacity] into a LOCAL
+ *                       result buffer of the same shape, which the caller copies back to the sources'
+ *                       results[owner][segment_capacity]; exchange_unpermute then restores input order
+ *                       (lookups are staged with slices = 1: position = owner * segment_capacity + i). */
+int cuco_b200_exchange_stage_plan(cuco_b200_table* t,
+                                  int64_t n_max,
+                                  int num_ranks,
+                                  int slices,
+                                  uint32_t* segment_capacity,
+                                  uint32_t* spill_capacity);
+int cuco_b200_exchange_stage(cuco_b200_table* t,
+                             const void* keys,
+                             const void* values,
+                             int64_t n,
+                             int keys_only,
+                             int slices,
+                             uint32_t segment_capacity,
+                             uint32_t spill_capacity,
+                             int num_ranks,
+                             int my_rank,
+                             uint64_t salt,
+                             void* stage,
+                             void* counts_local,
+                             void* position_local,
+                             void* spill,
+                             void* spill_index,
+                             void* spill_count,
+                             void* stream);
+/* Step 2, small part: stores counts_local[owner * slices + slice] into the owner's
+ * recv_counts[slice * num_ranks + my_rank] and *spill_count into every peer's flags[my_rank] (peer
+ * stores; the data blocks themselves go through cuco_b200_copy_async). */
+int cuco_b200_exchange_publish(const void* counts_local,
+                               const void* spill_count,
+                               void* const* peer_counts,
+                               void* const* peer_flags,
+                               int slices,
+                               uint32_t segment_capacity,
+                               int num_ranks,
+                               int my_rank,
+                               int source_major, /* != 0: recv_counts[my_rank * slices + slice] (fine mode) */
+                               void* stream);
+/* Fine mode of the staged exchange, for shards small enough that num_ranks x (L2 regions of the shard)
+ * stays within the router's bucket budget: the sources stage by (owner, L2 REGION) directly
+ * (exchange_stage with slices = *num_regions), blocks travel source-major into
+ * recv[source][region][segment_capacity], and exchange_probe probes a range of regions with their slots
+ * resident in L2 - the owner needs no regrouping pass of its own. *num_regions = 0: use exchange_apply. */
+int cuco_b200_exchange_fine_regions(cuco_b200_table* t, int num_ranks, uint32_t* num_regions);
+int cuco_b200_exchange_probe(cuco_b200_table* t,
+                             const void* segments,
+                             const void* counts_recv,
+                             uint32_t num_regions,
+                             uint32_t segment_capacity,
+                             int num_ranks,
+                             uint32_t region_begin,
+                             uint32_t region_count,
+                             int reduce_op,
+                             void* stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): device-to-device, local or through an
+ * NVLink peer mapping; runs on the copy engines, next to whatever kernels the SMs are running. */
+int cuco_b200_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int cuco_b200_exchange_apply(cuco_b200_table* t,
+                             const void* segments,
+                             const void* counts_recv,
+                             uint32_t segment_capacity,
+                             int num_ranks,
+                             int slice,
+                             int slices,
+                             int reduce_op,
+                             void* stream);
+int cuco_b200_exchange_lookup_local(cuco_b200_table* t,
+                                    const void* segments,
+                                    const void* counts_recv,
+                                    void* results,
+                                    uint32_t segment_capacity,
+                                    int num_ranks,
+                                    int what,
+                                    void* stream);
+
 /* out[index[i]] = in[i] for i < n (elem_bytes in {1,4,8}); un-permutes routed lookup results. */
 int cuco_b200_scatter_by_index(
   const void* in, const int64_t* index, void* out, int elem_bytes, int64_t n, void* stream);

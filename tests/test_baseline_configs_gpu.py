@@ -169,8 +169,10 @@ def test_insert_after_erase_follows_cuco(kind, native_lib, reference_lib):
     log["oracle"].append(ref.size()); log["oracle"].append(ref.contains(keys).tolist())
     assert log["ours"] == log["cuco"]
     assert log["ours"] == log["oracle"]
-    # the scenario is not vacuous: at least one re-insert duplicated its key
-    assert sum(log["cuco"][41:41 + len(keep)]) > 0
+    if kind == _cabi.MAP_I64_LP1:
+        # the scenario is not vacuous: with one-slot probe steps at least one re-insert duplicated its key
+        # (with cg_size > 1 an EQUAL report anywhere in the step outranks the erased slot, ref_impl.cuh:455-458)
+        assert sum(log["cuco"][41:41 + len(keep)]) > 0
 
 
 def cb_make(kind, lib, capacity):

@@ -66,10 +66,17 @@ def reset_tuning(native_lib):
     native_lib.set_blocking(-1, 16)
 
 
+# blocked: force the L2-blocked count / retrieve (include/cuco/b200/blocked_match.cuh) with tiny 16 KiB
+# regions, so that even these small tables are staged by region and probed region by region
+BLOCKING = [(-1, 16), (1, -16)]
+
+
+@pytest.mark.parametrize("blocking", BLOCKING)
 @pytest.mark.parametrize("generic", [0, 1])
 @pytest.mark.parametrize("kind", MULTISET_KINDS)
-def test_multiset_matches_oracle(kind, generic, native_lib):
+def test_multiset_matches_oracle(kind, generic, blocking, native_lib):
     native_lib.set_tuning(12, 0, 1, 0, generic, 1, 0)
+    native_lib.set_blocking(*blocking)
     k = cb.KINDS[kind]
     n = 20_000
     keys = skewed_keys(n, n // 4, 11)
@@ -121,8 +128,10 @@ def test_multiset_insert_if_and_blocked_insert(kind, native_lib):
         t.close()
 
 
+@pytest.mark.parametrize("blocking", BLOCKING)
 @pytest.mark.parametrize("kind", SET_KINDS)
-def test_set_retrieve_matches_oracle(kind, native_lib):
+def test_set_retrieve_matches_oracle(kind, blocking, native_lib):
+    native_lib.set_blocking(*blocking)
     k = cb.KINDS[kind]
     n = 30_000
     keys = np.random.default_rng(13).integers(0, n, size=n, dtype=np.int64)
@@ -141,9 +150,11 @@ def test_set_retrieve_matches_oracle(kind, native_lib):
     t.close()
 
 
+@pytest.mark.parametrize("blocking", BLOCKING)
 @pytest.mark.parametrize("kind", MULTISET_KINDS + SET_KINDS)
-def test_matches_equal_cuco_itself(kind, native_lib, reference_lib):
+def test_matches_equal_cuco_itself(kind, blocking, native_lib, reference_lib):
     """Same calls into our build and into cuco's own build of the same shim."""
+    native_lib.set_blocking(*blocking)
     k = cb.KINDS[kind]
     n = 40_000
     keys = skewed_keys(n, n // 5, 15)
@@ -226,9 +237,11 @@ def test_native_matches_golden_fixtures(kind, native_lib):
         assert np.array_equal(got[name], g[name]), name
 
 
-def test_empty_inputs_and_high_multiplicity(native_lib):
+@pytest.mark.parametrize("blocking", BLOCKING)
+def test_empty_inputs_and_high_multiplicity(blocking, native_lib):
     """n == 0 returns without launching (impl.cuh:335 convention); a key stored more often than the
     retrieve kernel keeps matches in registers takes the second-walk path."""
+    native_lib.set_blocking(*blocking)
     kind = _cabi.MULTISET_I64_LP1_W2
     k = cb.KINDS[kind]
     t = make(kind, native_lib, capacity=4096)
@@ -248,6 +261,13 @@ def test_empty_inputs_and_high_multiplicity(native_lib):
     assert np.array_equal(np.bincount(p.cpu().numpy(), minlength=probes.size)[: mult.size], mult)
     p, m = t.retrieve(dev(probes, k.key), outer=True)
     assert p.numel() == int(mult.sum()) + 3 and int((m == -1).sum().item()) == 3
+    # one hot probe key: with the blocked path its region's segment overflows - first into the spill
+    # list (100 k probes), then past it (300 k probes: the whole batch is redone by the direct kernel)
+    for hot in (100_000, 300_000):
+        batch = torch.cat([torch.full((hot,), 6, dtype=k.key, device="cuda"), dev(probes, k.key)])
+        assert t.count(batch) == hot * 33 + int(mult.sum())
+        p, m = t.retrieve(batch[: hot // 10 + 11])
+        assert torch.equal(p, m) and p.numel() == (hot // 10 + 11) * 33
     t.close()
     s = make(_cabi.SET_I64_DH4, native_lib, capacity=1000)
     p, m = s.retrieve(empty)

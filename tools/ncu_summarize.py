@@ -43,6 +43,8 @@ def main():
     tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else "r02"
     per = {}
     for l in load(path):
+        if "b200::" not in l["kernel"] and "cuco::" not in l["kernel"]:
+            continue  # torch's own kernels (input generation, checks) are not part of the hot path
         k = short(l["kernel"])
         per.setdefault(k, {"ns": [], "dram": []})
         per[k]["ns"].append(l.get("gpu__time_duration.sum", 0.0))
@@ -58,7 +60,7 @@ def main():
         print(f"{k:40s} x{v['launches']:<3d} {v['ms_median']:8.3f} ms  {v['dram_bytes_median'] / 1e9:8.3f} GB")
     traffic_file = ROOT / "profiles" / "traffic.json"
     traffic = json.loads(traffic_file.read_text()) if traffic_file.exists() else {}
-    traffic.setdefault(arm, {})
+    traffic[arm] = {} if arm == "native" else traffic.get(arm, {})
     for k, v in table.items():
         if v["ms_median"] > 0.05:
             traffic[arm][k] = int(v["dram_bytes_median"])
