@@ -1581,7 +1581,7 @@ CUCO_KERNEL __launch_bounds__(BlockSize) void erase_kernel(InputIt first, index_
           auto const slot  = chunk_slot<slot_type>(raw[j], i);
           auto const state = engine.classify_lookup(key[j].value, Engine::key_of(slot));
           if (state == equal_result::EQUAL) {
-            engine.retire_slot(engine.slots() + (cur[j].slot + (i - begin_off)), Engine::key_of(slot));
+            engine.retire_observed(engine.slots() + (cur[j].slot + (i - begin_off)), slot);
             done = true;
           } else if (state == equal_result::EMPTY) {
             done = true;

@@ -823,7 +823,7 @@ class probe_engine {
       auto const state = classify_lookup(key, key_of(slot));
       if (state == equal_result::EMPTY) { return true; }
       if (state != equal_result::EQUAL) { return false; }
-      erased = retire_slot(slots() + index, key_of(slot));
+      erased = retire_observed(slots() + index, slot);
       return true;
     });
     return erased;
@@ -1117,9 +1117,28 @@ class probe_engine {
 
  public:
   /// key -> erased sentinel (payload reset to the empty payload); true iff we made the transition.
+  /// Same, for a caller that already holds the slot image it observed: packed slots go straight to
+  /// the one CAS (no second load of the slot; the claim and the payload reset are one 32/64/128-bit
+  /// atomic), the rest is `retire_slot`.
+  __device__ bool retire_observed(value_type* address, value_type const& observed) noexcept
+  {
+    if constexpr (single_cas) {
+      value_type expected = observed;
+      auto const key      = key_of(observed);
+      while (eq_(key, key_of(expected)) && !same_bits(key_of(expected), erased_key_)) {
+        auto const seen = cas_slot<Scope>(address, expected, erased_slot_sentinel());
+        if (same_bits(seen, expected)) { return true; }
+        expected = seen;
+      }
+      return false;
+    } else {
+      return this->retire_slot(address, key_of(observed));
+    }
+  }
+
   __device__ bool retire_slot(value_type* address, key_type observed_key) noexcept
   {
-    if constexpr (has_payload && sizeof(value_type) > 8) {
+    if constexpr (has_payload && sizeof(value_type) > 8 && !single_cas) {
       cuda::atomic_ref<key_type, Scope> key_ref{address->first};
       if (key_ref.compare_exchange_strong(observed_key, erased_key_, cuda::memory_order_relaxed)) {
         cuda::atomic_ref<decltype(address->second), Scope> payload_ref{address->second};

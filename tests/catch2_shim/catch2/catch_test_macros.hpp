@@ -48,7 +48,13 @@ struct skipped : std::exception {
 /// GENERATE yields, and what the run discovered (siblings per depth, values per generator).
 struct run_state {
   std::vector<int> section_path;      // target child index per depth
-  std::vector<int> section_seen;      // children seen at each depth inside the entered parent
+  // Children discovered at each depth inside the entered parent, in first-visit order. A section is
+  // identified by its source line and name, as in Catch2 (SectionTracker: name + location): a SECTION
+  // macro that control flow reaches several times in one run (a helper called in a loop or thrice in a
+  // row, e.g. tests/static_multiset/retrieve_test.cu:152-154) is ONE section, entered on its first visit
+  // of the run in which it is the target and skipped on every other visit.
+  std::vector<std::vector<std::string>> section_seen;
+  std::vector<bool> section_entered;  // the target child of this depth has already run in this run
   int depth = 0;
   std::vector<int> generator_choice;  // chosen value index per GENERATE call (in call order)
   std::vector<int> generator_size;
@@ -64,24 +70,41 @@ inline run_state*& current()
 
 class section {
  public:
-  explicit section(char const*)
+  section(char const* name, int line)
   {
     auto& s = *current();
-    if (static_cast<int>(s.section_seen.size()) <= s.depth) { s.section_seen.resize(s.depth + 1, 0); }
-    int const index = s.section_seen[s.depth]++;
+    if (static_cast<int>(s.section_seen.size()) <= s.depth) {
+      s.section_seen.resize(s.depth + 1);
+      s.section_entered.resize(s.depth + 1, false);
+    }
+    std::string const id = std::to_string(line) + ":" + name;
+    auto& seen           = s.section_seen[s.depth];
+    int index            = -1;
+    for (std::size_t i = 0; i < seen.size(); ++i) {
+      if (seen[i] == id) { index = static_cast<int>(i); }
+    }
+    if (index < 0) {
+      index = static_cast<int>(seen.size());
+      seen.push_back(id);
+    }
     if (static_cast<int>(s.section_path.size()) <= s.depth) {
       // first visit of this depth in this run: take the first child
-      if (index == 0) {
+      if (index == 0 && !s.section_entered[s.depth]) {
         s.section_path.push_back(0);
         entered_ = true;
       }
     } else {
-      entered_ = s.section_path[s.depth] == index;
+      entered_ = s.section_path[s.depth] == index && !s.section_entered[s.depth];
     }
     if (entered_) {
+      s.section_entered[s.depth] = true;
       ++s.depth;
-      if (static_cast<int>(s.section_seen.size()) <= s.depth) { s.section_seen.resize(s.depth + 1, 0); }
-      s.section_seen[s.depth] = 0;
+      if (static_cast<int>(s.section_seen.size()) <= s.depth) {
+        s.section_seen.resize(s.depth + 1);
+        s.section_entered.resize(s.depth + 1, false);
+      }
+      s.section_seen[s.depth].clear();
+      s.section_entered[s.depth] = false;
     }
   }
   ~section()
@@ -126,6 +149,7 @@ inline long run_test_case(test_case const& tc, long& assertions, bool& was_skipp
   while (true) {
     s.section_path     = next_path;
     s.section_seen.clear();
+    s.section_entered.clear();
     s.depth            = 0;
     s.generator_choice = choices;
     s.generator_calls  = 0;
@@ -149,7 +173,7 @@ inline long run_test_case(test_case const& tc, long& assertions, bool& was_skipp
     bool more_sections = false;
     while (!next_path.empty()) {
       auto const d = next_path.size() - 1;
-      int const siblings = d < s.section_seen.size() ? s.section_seen[d] : 0;
+      int const siblings = d < s.section_seen.size() ? static_cast<int>(s.section_seen[d].size()) : 0;
       if (next_path[d] + 1 < siblings) {
         ++next_path[d];
         more_sections = true;
@@ -215,7 +239,7 @@ inline std::string first_string(char const* name, char const* = "") { return nam
 
 #define TEST_CASE(...) CATCH2_SHIM_TEST_CASE(CATCH2_SHIM_UNIQUE(catch2_shim_test_), __VA_ARGS__)
 
-#define SECTION(...) if (::catch2_shim::section CATCH2_SHIM_UNIQUE(catch2_shim_section_){#__VA_ARGS__})
+#define SECTION(...) if (::catch2_shim::section CATCH2_SHIM_UNIQUE(catch2_shim_section_){#__VA_ARGS__, __LINE__})
 
 #define REQUIRE(...)       ::catch2_shim::report(static_cast<bool>(__VA_ARGS__), true, __FILE__, __LINE__, "REQUIRE(" #__VA_ARGS__ ")")
 #define REQUIRE_FALSE(...) ::catch2_shim::report(!static_cast<bool>(__VA_ARGS__), true, __FILE__, __LINE__, "REQUIRE_FALSE(" #__VA_ARGS__ ")")

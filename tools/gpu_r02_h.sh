@@ -3,7 +3,11 @@
 # traced weak-scaling bench for fine and coarse mode
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_staged_exchange_gpu.py tests/test_baseline_configs_gpu.py -x -q > gpurun_out/r02h_pytest.log 2>&1
+for t in static_multiset__retrieve_test static_map__erase_test static_set__retrieve_all_test static_map__rehash_test; do
+  timeout 200 tests/_build/reftests/${t}_native > gpurun_out/r02h_${t}.log 2>&1; echo "$t rc=$?"; tail -n 2 gpurun_out/r02h_${t}.log | cut -c1-200
+done
+timeout 300 python tools/next_rows_bench.py > gpurun_out/r02_next_rows.jsonl 2> gpurun_out/r02_next_rows.err; cat gpurun_out/r02_next_rows.jsonl
+timeout 900 python -m pytest tests/test_staged_exchange_gpu.py tests/test_baseline_configs_gpu.py tests/test_matches_gpu.py tests/test_parity_gpu.py -x -q > gpurun_out/r02h_pytest.log 2>&1
 echo "pytest rc=$?"; tail -n 6 gpurun_out/r02h_pytest.log | cut -c1-250
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $RUN tests/multi_gpu_check.py 2000000 > gpurun_out/r02h_multi_gpu_check_${N}.log 2>&1
