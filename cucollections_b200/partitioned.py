@@ -207,7 +207,11 @@ class FusedExchange:
         if n > self.n_max:
             raise ValueError(f"batch of {n} exceeds the exchange buffers sized for {self.n_max}")
         main = torch.cuda.current_stream(self.device)
-        chunks = self._chunks(n) or [(0, 0)]  # an empty batch still takes part in the barriers
+        # every rank runs all K lanes in every call (empty chunks included): ranks with different batch
+        # sizes would otherwise disagree on the number of barriers, and a lane that is skipped would keep
+        # the spill flags of an earlier call
+        chunks = self._chunks(n)
+        chunks += [(n, n)] * (self.K - len(chunks))
         if self.side is None:
             for i, (lo, hi) in enumerate(chunks):
                 lane = self.lanes[i % self.K]
@@ -417,6 +421,17 @@ class StagedExchange:
         # probe kernels' CTAs, or a landed slice would be announced late
         self.copy_in = torch.cuda.Stream(dev, priority=-1)    # source -> owner transfers
         self.copy_back = torch.cuda.Stream(dev, priority=-1)  # owner -> source transfers (lookup results)
+        # measured at 8 GPUs (profiles/r02_exchange_sweep_8gpu.txt): 1 / 4 / 8 side streams -> 178 / 176 / 158
+        # Gops/s: the copies of one phase do not gain from running side by side, 8 at once lose to ingress
+        # contention. One stream is the default; the fan-out stays for other topologies.
+        fan = int(os.environ.get("CUCO_B200_COPY_STREAMS", "1"))
+        self.fan = [torch.cuda.Stream(dev, priority=-1) for _ in range(max(0, fan))]       # source -> owner
+        self.fan_back = [torch.cuda.Stream(dev, priority=-1) for _ in range(max(0, fan))]  # owner -> source
+        self.fork_events = [torch.cuda.Event() for _ in range(64)]
+        self.join_events = [torch.cuda.Event() for _ in range(256)]
+        self.fork_next = self.join_next = 0
+        self.apply_streams = [torch.cuda.Stream(dev) for _ in range(int(os.environ.get("CUCO_B200_APPLY_STREAMS", "1")) - 1)]
+        self.apply_done = [torch.cuda.Event() for _ in self.apply_streams]
         self.staged = torch.cuda.Event()
         self.consumed = torch.cuda.Event()
         self.slice_landed = [torch.cuda.Event() for _ in range(self.G)]
@@ -465,6 +480,30 @@ class StagedExchange:
     def _copy(self, dst, src, nbytes, stream):
         self.lib.check(self.lib.copy_async(C.c_void_p(dst), C.c_void_p(src), nbytes, self._s(stream)))
 
+    def _fan_out(self, copies, stream, fan=None):
+        """Issues the (dst, src, bytes) copies of one phase. On `stream` alone they would run one after
+        the other, each paying the fixed cost of a peer copy (measured at 8 GPUs: 8 x 3 MB took 0.5 ms);
+        spread over `fan` side streams they overlap and keep several copy engines busy. Fork / join with
+        events, so that for `stream` the phase still looks like one operation."""
+        fan = self.fan if fan is None else fan
+        if stream is None or len(fan) <= 1 or len(copies) <= 1:
+            for dst, src, nbytes in copies:
+                self._copy(dst, src, nbytes, stream)
+            return
+        fork = self.fork_events[self.fork_next % len(self.fork_events)]
+        self.fork_next += 1
+        fork.record(stream)
+        used = min(len(fan), len(copies))
+        for j in range(used):
+            fan[j].wait_event(fork)
+        for i, (dst, src, nbytes) in enumerate(copies):
+            self._copy(dst, src, nbytes, fan[i % used])
+        for j in range(used):
+            join = self.join_events[(self.join_next + j) % len(self.join_events)]
+            join.record(fan[j])
+            stream.wait_event(join)
+        self.join_next += used
+
     # ---- mutations: the steps (driven in lock-step by the simulated-rank tests) --------------------
     def stage_pairs(self, pairs):
         n = pairs.shape[0]
@@ -492,6 +531,7 @@ class StagedExchange:
         rank-rotated order (at any moment every rank writes to a different peer)."""
         block = self.cap * self.slot_bytes
         b0, b1 = self._buckets(g)
+        copies = []
         for i in range(self.P):
             o = (self.me + i) % self.P
             src = self.stage.data_ptr() + (o * self.B + b0) * block
@@ -499,8 +539,9 @@ class StagedExchange:
                 dst = self.peers()[o] + self.off_recv + (self.me * self.B + b0) * block
             else:           # recv[slice][source][cap], one slice per phase
                 dst = self.peers()[o] + self.off_recv + (b0 * self.P + self.me) * block
-            with torch.cuda.device(self.device):
-                self._copy(dst, src, (b1 - b0) * block, stream)
+            copies.append((dst, src, (b1 - b0) * block))
+        with torch.cuda.device(self.device):
+            self._fan_out(copies, stream)
 
     def apply_slice(self, g, reduce_op=-1):
         block = self.cap * self.slot_bytes
@@ -533,10 +574,27 @@ class StagedExchange:
                 self.t.barrier(0)                    # slice g has landed on every owner
                 self.slice_landed[g].record(self.copy_in)
                 self._tick(f"mutate: slice {g} landed", self.copy_in)
-        for g in range(self.G):
-            main.wait_event(self.slice_landed[g])
-            self.apply_slice(g, reduce_op)
-            self._tick(f"mutate: slice {g} applied")
+        if not self.apply_streams:
+            for g in range(self.G):
+                main.wait_event(self.slice_landed[g])
+                self.apply_slice(g, reduce_op)
+                self._tick(f"mutate: slice {g} applied")
+        else:
+            # slices alternate between the caller's stream and side streams: the regrouping pass of slice
+            # g + 1 fills the tail of the probe of slice g (slices touch disjoint parts of the table)
+            lanes = [main] + self.apply_streams
+            self.staged.record(main)
+            for st in self.apply_streams:
+                st.wait_event(self.staged)  # everything the caller queued before this call
+            for g in range(self.G):
+                st = lanes[g % len(lanes)]
+                with torch.cuda.stream(st):
+                    st.wait_event(self.slice_landed[g])
+                    self.apply_slice(g, reduce_op)
+                    self._tick(f"mutate: slice {g} applied", st)
+            for i, st in enumerate(self.apply_streams):
+                self.apply_done[i].record(st)
+                main.wait_event(self.apply_done[i])
         self.consumed.record(main)
         total, mine = self._spilled(mutation=True)
         if total == 0:
@@ -564,10 +622,9 @@ class StagedExchange:
                 self._ptr_array(self.off_kflags + lane.id * pad4), 1, self.cap_l, self.P, self.me, 0,
                 self._s(stream)))
             block = self.cap_l * self.key_bytes
-            for i in range(self.P):
-                o = (self.me + i) % self.P
-                self._copy(self.peers()[o] + self.off_keys + lane.id * self.keys_lane + self.me * block,
-                           lane.stage.data_ptr() + o * block, block, stream)
+            self._fan_out([(self.peers()[o] + self.off_keys + lane.id * self.keys_lane + self.me * block,
+                            lane.stage.data_ptr() + o * block, block)
+                           for o in ((self.me + i) % self.P for i in range(self.P))], stream)
 
     def answer_keys(self, lane, what):
         pad4 = (self.P * 4 + 255) // 256 * 256
@@ -581,10 +638,9 @@ class StagedExchange:
         rbytes = self._result_bytes(what)
         block = self.cap_l * rbytes
         with torch.cuda.device(self.device):
-            for i in range(self.P):
-                s = (self.me + i) % self.P
-                self._copy(self.peers()[s] + self.off_back + lane.id * self.back_lane + self.me * block,
-                           lane.results.data_ptr() + s * block, block, stream)
+            self._fan_out([(self.peers()[s] + self.off_back + lane.id * self.back_lane + self.me * block,
+                            lane.results.data_ptr() + s * block, block)
+                           for s in ((self.me + i) % self.P for i in range(self.P))], stream, self.fan_back)
 
     def _result_bytes(self, what):
         k = self.table.kind

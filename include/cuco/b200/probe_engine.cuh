@@ -745,8 +745,10 @@ class probe_engine {
         return try_claim(target, expected, native_value(v), key_of(v));
       });
     if constexpr (has_payload) {
-      // a two-step writer (padded slots, insert_or_assign/apply) may not have published yet
-      if (!res.second || !single_cas) { wait_for_payload(res.first->second, empty_slot_.second); }
+      // a two-step writer (padded slots, insert_or_assign/apply) may not have published yet. Never
+      // after our OWN successful insert: try_claim has stored the payload by then, and a payload equal
+      // to the sentinel would spin forever
+      if (!res.second) { wait_for_payload(res.first->second, empty_slot_.second); }
     }
     return {iterator{res.first}, res.second};
   }
@@ -963,7 +965,7 @@ class probe_engine {
       return try_claim(t, e, native_value(v), key_of(v));
     });
     if constexpr (has_payload) {
-      if (!res.second || !single_cas) {
+      if (!res.second) {  // see scalar_insert_and_find: never after the tile's own successful insert
         if (tile.thread_rank() == 0) { wait_for_payload(res.first->second, empty_slot_.second); }
         tile.sync();
       }
