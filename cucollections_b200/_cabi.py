@@ -81,6 +81,7 @@ _PROTOTYPES = {
     "cuco_b200_exchange_fine_regions": (_int, [_vp, _int, _pu32]),
     "cuco_b200_exchange_probe": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _u32, _u32, _int, _vp]),
     "cuco_b200_copy_async": (_int, [_vp, _vp, _i64, _vp]),
+    "cuco_b200_push_async": (_int, [_pvp, _pvp, C.POINTER(C.c_int64), _int, _int, _vp]),
     "cuco_b200_exchange_apply": (_int, [_vp, _vp, _vp, _u32, _int, _int, _int, _int, _vp]),
     "cuco_b200_exchange_lookup_local": (_int, [_vp, _vp, _vp, _vp, _u32, _int, _int, _vp]),
     "cuco_b200_set_tuning": (_int, [_int, _int, _int, _int, _int, _int, _int]),

@@ -903,6 +903,70 @@ int cuco_b200_exchange_publish(const void* counts_local,
   });
 }
 
+#if !defined(CUCO_SHIM_REFERENCE)
+namespace {
+constexpr int push_max_copies = 16;
+struct push_job {
+  uint4* dst[push_max_copies];
+  uint4 const* src[push_max_copies];
+  unsigned long long vectors[push_max_copies];  // 16-byte units per copy
+};
+
+/// blockIdx.y = copy, the CTAs of a row stride over that copy: plain 16-byte loads and stores, four in
+/// flight per thread. The destinations may be peer mappings (NVLink): a handful of CTAs keeps the links
+/// busy, and one launch replaces the fixed cost of a cudaMemcpyAsync per peer.
+__global__ void __launch_bounds__(256) push_kernel(push_job job)
+{
+  auto const* src       = job.src[blockIdx.y];
+  auto* dst             = job.dst[blockIdx.y];
+  auto const n          = job.vectors[blockIdx.y];
+  auto const stride     = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  unsigned long long i  = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    uint4 const a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i]              = a;
+    dst[i + stride]     = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n; i += stride) {
+    dst[i] = src[i];
+  }
+}
+}  // namespace
+#endif
+
+int cuco_b200_push_async(void* const* dst,
+                         const void* const* src,
+                         const int64_t* bytes,
+                         int num_copies,
+                         int ctas_per_copy,
+                         void* stream)
+{
+  return guarded([&] {
+#if defined(CUCO_SHIM_REFERENCE)
+    (void)dst, (void)src, (void)bytes, (void)num_copies, (void)ctas_per_copy, (void)stream;
+    throw std::invalid_argument("the exchange path exists in the native build only");
+#else
+    require(dst && src && bytes && num_copies >= 0 && num_copies <= push_max_copies && ctas_per_copy >= 1,
+            "bad argument");
+    if (num_copies == 0) { return; }
+    push_job job{};
+    for (int i = 0; i < num_copies; ++i) {
+      require(bytes[i] >= 0 && bytes[i] % 16 == 0 && reinterpret_cast<std::uintptr_t>(dst[i]) % 16 == 0 &&
+                reinterpret_cast<std::uintptr_t>(src[i]) % 16 == 0,
+              "copies must be 16-byte aligned multiples of 16 bytes");
+      job.dst[i]     = static_cast<uint4*>(dst[i]);
+      job.src[i]     = static_cast<uint4 const*>(src[i]);
+      job.vectors[i] = static_cast<unsigned long long>(bytes[i]) / 16;
+    }
+    push_kernel<<<dim3{static_cast<unsigned>(ctas_per_copy), static_cast<unsigned>(num_copies)}, 256, 0,
+                  static_cast<cudaStream_t>(stream)>>>(job);
+    check_launch();
+#endif
+  });
+}
+
 int cuco_b200_copy_async(void* dst, const void* src, int64_t bytes, void* stream)
 {
   return guarded([&] {

@@ -425,12 +425,21 @@ class StagedExchange:
         # Gops/s: the copies of one phase do not gain from running side by side, 8 at once lose to ingress
         # contention. One stream is the default; the fan-out stays for other topologies.
         fan = int(os.environ.get("CUCO_B200_COPY_STREAMS", "1"))
+        # blocks up to this size travel by push kernel (0 = always the copy engines)
+        self.push_bytes = int(os.environ.get("CUCO_B200_PUSH_MIB", "8")) << 20
+        self.push_ctas = int(os.environ.get("CUCO_B200_PUSH_CTAS", "8"))
         self.fan = [torch.cuda.Stream(dev, priority=-1) for _ in range(max(0, fan))]       # source -> owner
         self.fan_back = [torch.cuda.Stream(dev, priority=-1) for _ in range(max(0, fan))]  # owner -> source
         self.fork_events = [torch.cuda.Event() for _ in range(64)]
         self.join_events = [torch.cuda.Event() for _ in range(256)]
         self.fork_next = self.join_next = 0
-        self.apply_streams = [torch.cuda.Stream(dev) for _ in range(int(os.environ.get("CUCO_B200_APPLY_STREAMS", "1")) - 1)]
+        # streams the slices are applied on, round-robin. Measured: 2 streams gain 4 % in fine mode (probe-only
+        # applies: the next probe fills the tail of the previous one, 2 GPUs 3.60 -> 3.45 ms) but cost 20 % on the
+        # 16.5 GB shards of C4 in coarse mode (two regroup + probe pairs at once evict each other's L2 regions:
+        # 21.0 -> 26.1 ms per 500 M pairs at 8 GPUs), so: 2 in fine mode, 1 in coarse mode
+        default_apply = "2" if self.fine else "1"
+        self.apply_streams = [torch.cuda.Stream(dev)
+                              for _ in range(int(os.environ.get("CUCO_B200_APPLY_STREAMS", default_apply)) - 1)]
         self.apply_done = [torch.cuda.Event() for _ in self.apply_streams]
         self.staged = torch.cuda.Event()
         self.consumed = torch.cuda.Event()
@@ -485,6 +494,14 @@ class StagedExchange:
         the other, each paying the fixed cost of a peer copy (measured at 8 GPUs: 8 x 3 MB took 0.5 ms);
         spread over `fan` side streams they overlap and keep several copy engines busy. Fork / join with
         events, so that for `stream` the phase still looks like one operation."""
+        if copies and max(c[2] for c in copies) <= self.push_bytes and len(copies) <= 16:
+            # small blocks (lookup chunks): one push kernel instead of a peer copy per destination
+            n = len(copies)
+            dst = (C.c_void_p * n)(*[c[0] for c in copies])
+            src = (C.c_void_p * n)(*[c[1] for c in copies])
+            size = (C.c_int64 * n)(*[c[2] for c in copies])
+            self.lib.check(self.lib.push_async(dst, src, size, n, self.push_ctas, self._s(stream)))
+            return
         fan = self.fan if fan is None else fan
         if stream is None or len(fan) <= 1 or len(copies) <= 1:
             for dst, src, nbytes in copies:

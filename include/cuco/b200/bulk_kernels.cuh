@@ -38,12 +38,50 @@
 #include <cooperative_groups/reduce.h>
 
 #include <cstdint>
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 namespace cuco::b200 {
 
 using cuco::detail::index_type;
 
 /// Identity predicate for the un-stencilled entry points.
+/// The stream-ordered pool all containers (and the whole-table passes of table_scan.cuh) on the current
+/// device draw their per-call scratch from:
+/// one per device for the life of the process (a pool per container costs a 2 MiB granule and a
+/// driver round trip each - the reference's shared_memory_test builds 1000 maps). Freed blocks stay
+/// cached up to CUCO_B200_SCRATCH_KEEP_MIB (default 4096) so that back-to-back bulk calls do not
+/// pay cudaMalloc; anything above goes back to the driver at the next synchronisation.
+[[nodiscard]] inline cudaMemPool_t device_scratch_pool() noexcept
+{
+  constexpr int max_devices = 64;
+  static std::mutex guard;
+  static cudaMemPool_t pools[max_devices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= max_devices) { return nullptr; }
+  std::lock_guard<std::mutex> lock{guard};
+  if (pools[dev] == nullptr) {
+    cudaMemPoolProps props{};
+    props.allocType     = cudaMemAllocationTypePinned;
+    props.handleTypes   = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id   = dev;
+    if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) {
+      cudaGetLastError();
+      pools[dev] = nullptr;
+      return nullptr;
+    }
+    std::uint64_t keep = std::uint64_t{4096} << 20;
+    if (char const* s = std::getenv("CUCO_B200_SCRATCH_KEEP_MIB")) {
+      keep = static_cast<std::uint64_t>(std::max(0, std::atoi(s))) << 20;
+    }
+    cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pools[dev];
+}
+
+
 struct always_true {
   template <typename T>
   __host__ __device__ constexpr bool operator()(T const&) const noexcept

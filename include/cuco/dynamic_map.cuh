@@ -139,7 +139,10 @@ class dynamic_map {
     submaps_.front()->contains_async(first, last, output_begin, stream);
     if (submaps_.size() > 1) {
       bool* more = nullptr;
-      CUCO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&more), static_cast<std::size_t>(n), stream.get()));
+      auto const pool = cuco::b200::device_scratch_pool();  // cached blocks; the default pool releases at every sync
+      CUCO_EXPECTS(pool != nullptr, "no stream-ordered memory pool on this device");
+      CUCO_CUDA_TRY(cudaMallocFromPoolAsync(
+        reinterpret_cast<void**>(&more), static_cast<std::size_t>(n), pool, stream.get()));
       auto const grid = static_cast<unsigned>(
         std::min<cuco::detail::index_type>(cuco::detail::int_div_ceil(n, cuco::detail::index_type{256}), 1 << 20));
       for (std::size_t i = 1; i < submaps_.size(); ++i) {

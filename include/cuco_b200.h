@@ -403,6 +403,15 @@ int cuco_b200_exchange_probe(cuco_b200_table* t,
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): device-to-device, local or through an
  * NVLink peer mapping; runs on the copy engines, next to whatever kernels the SMs are running. */
 int cuco_b200_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* The same for up to 16 copies at once with ONE small kernel (ctas_per_copy CTAs of 256 threads per copy,
+ * 16-byte vectors; every pointer 16-byte aligned, every size a multiple of 16): for the small blocks of
+ * the lookup chunks, where eight peer copies cost their fixed latency rather than bandwidth. */
+int cuco_b200_push_async(void* const* dst,
+                         const void* const* src,
+                         const int64_t* bytes,
+                         int num_copies,
+                         int ctas_per_copy,
+                         void* stream);
 int cuco_b200_exchange_apply(cuco_b200_table* t,
                              const void* segments,
                              const void* counts_recv,

@@ -103,7 +103,9 @@ def lookup_all(ranks, queries, outs, what):
 @pytest.mark.parametrize("kind,P,slices,lanes,region_kib", [
     (_cabi.MAP_I64_LP1, 3, 4, 2, 16), (_cabi.MAP_I64_DH8, 2, 2, 1, 64), (_cabi.MAP_I32_LP4, 4, 3, 3, 16),
     (_cabi.SET_I64_DH4, 2, 2, 2, 16), (_cabi.MAP_I64_LP1_X64, 8, 5, 4, 4), (_cabi.MAP_I64_LP1, 1, 2, 2, 16)])
-def test_staged_exchange_with_simulated_ranks(kind, P, slices, lanes, region_kib, mode, native_lib):
+def test_staged_exchange_with_simulated_ranks(kind, P, slices, lanes, region_kib, mode, native_lib, monkeypatch):
+    # blocks travel by cudaMemcpyAsync in the coarse runs and by the push kernel in the fine ones
+    monkeypatch.setenv("CUCO_B200_PUSH_MIB", "0" if mode == "coarse" else "8")
     k = cb.KINDS[kind]
     is_map = k.value is not None
     n = 60_000  # per rank
