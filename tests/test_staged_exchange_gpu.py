@@ -194,3 +194,26 @@ def test_staged_exchange_spills_a_hot_key(native_lib):
     assert np.array_equal(outs[1].cpu().numpy(), cold)
     for r in ranks:
         r.table.close()
+
+
+def test_staged_lookup_with_short_and_empty_batches(native_lib):
+    """Ranks whose batch is shorter than a lane - or empty - still run every lane (empty chunks), so the
+    barriers of the multi-process path match; answers stay correct for the ranks that do have keys."""
+    P, n, lanes = 3, 30_000, 3
+    kind = _cabi.MAP_I64_LP1
+    ranks = build_ranks(native_lib, kind, P, n, 2, lanes, "coarse")
+    ref = oracle.Table.for_kind(kind, 4 * n * P, 0.0)
+    batches = []
+    for me in range(P):
+        keys = keyset(kind, [n, 11, 0][me], 70 + me, hi=2 * n)   # full, shorter than one lane, empty
+        ref.insert(keys, keys + 5)
+        batches.append(dev(np.stack([keys, keys + 5], axis=1).reshape(-1, 2), torch.int64))
+    assert all(total == 0 for total, _ in mutate_all(ranks, batches))
+    assert sum(r.table.size() for r in ranks) == ref.size()
+    queries = [keyset(kind, m, 80 + me, hi=3 * n) for me, m in enumerate([0, n, 7])]
+    outs = [torch.full((q.shape[0],), -7, dtype=torch.int64, device="cuda") for q in queries]
+    assert all(total == 0 for total, _ in lookup_all(ranks, [dev(q, torch.int64) for q in queries], outs, 0))
+    for me in range(P):
+        assert np.array_equal(outs[me].cpu().numpy(), ref.find(queries[me])), me
+    for r in ranks:
+        r.table.close()
