@@ -7,6 +7,7 @@
 //   tests/utility/extent_test.cu:26-55                          (1234 -> 314 windows for cg 2, window 4)
 //   tests/utility/fast_int_test.cu:27-61                        (div/mod identities)
 //   tests/static_map/capacity_test.cu, static_set/capacity_test.cu (rounding golds via valid_num_windows)
+#include <cuco/b200/bulk_kernels.cuh>
 #include <cuco/extent.cuh>
 #include <cuco/hash_functions.cuh>
 #include <cuco/pair.cuh>
@@ -284,9 +285,87 @@ void pair_layout()
 
 }  // namespace
 
+/// Host half of the partitioned / blocked paths: region_map (slot -> region and its exact inverse, also
+/// over a table slice) and exchange_owner (key -> owner rank), the two functions every rank must agree on.
+void exchange_host_logic()
+{
+  using cuco::b200::region_map;
+  std::uint64_t state = 0x243f6a8885a308d3ull;
+  auto next = [&] {
+    state ^= state << 13;
+    state ^= state >> 7;
+    state ^= state << 17;
+    return state;
+  };
+  for (std::uint64_t capacity : {std::uint64_t{4}, std::uint64_t{1000}, std::uint64_t{200039789}, std::uint64_t{1030100641},
+                                 std::uint64_t{4120042477ull}}) {
+    for (std::uint32_t regions : {2u, 7u, 99u, 197u, 1024u}) {
+      if (capacity < regions) { continue; }  // callers never ask for more regions than slots
+      for (std::uint64_t first : {std::uint64_t{0}, std::uint64_t{12345}}) {
+        auto const map = region_map::over(capacity, regions, first);
+        bool in_range = true, inverse = true, monotone = true;
+        std::uint64_t previous = first;
+        for (std::uint32_t r = 0; r < regions; ++r) {
+          auto const begin = map.region_begin(r);
+          monotone         = monotone && begin >= previous;
+          previous         = begin;
+          if (capacity >= 16ull * regions) {  // every region non-empty: its first slot maps to it, the slot before to r - 1
+            inverse = inverse && map(begin) == r && (r == 0 || map(begin - 1) + 1 == r);
+          }
+        }
+        for (int i = 0; i < 4000; ++i) {
+          std::uint64_t const slot = first + next() % capacity;
+          auto const r             = map(slot);
+          in_range                 = in_range && r < regions;
+          inverse                  = inverse && map.region_begin(r) <= slot;
+          if (r + 1 < regions) { inverse = inverse && slot < map.region_begin(r + 1); }
+        }
+        check(map.region_begin(0) == first, "region_map: region 0 starts at the slice");
+        check(in_range, "region_map: every slot maps below num_regions");
+        check(inverse, "region_map: region_begin is the exact inverse of the map");
+        check(monotone, "region_map: region starts are monotone");
+        check(map(first + capacity - 1) == regions - 1 || capacity < regions, "region_map: the last slot is in the last region");
+      }
+    }
+  }
+  for (std::uint32_t ranks : {1u, 2u, 3u, 8u, 16u}) {
+    std::vector<std::uint64_t> load(ranks, 0);
+    bool below = true;
+    constexpr std::uint64_t keys = 1000000;
+    for (std::uint64_t k = 0; k < keys; ++k) {
+      auto const owner = cuco::b200::exchange_owner(k, 0x9E3779B97F4A7C15ull, ranks);
+      below            = below && owner < ranks;
+      if (owner < ranks) { ++load[owner]; }
+    }
+    check(below, "exchange_owner: owner below the number of ranks");
+    bool balanced = true;
+    for (auto l : load) {
+      double const share = static_cast<double>(l) * ranks / keys;
+      balanced           = balanced && share > 0.98 && share < 1.02;
+    }
+    check(balanced, "exchange_owner: sequential keys spread within 2 % over the ranks");
+  }
+}
+
+void print_owners()
+{
+  std::printf("\"owners\": {");
+  bool first = true;
+  for (std::int64_t key : {std::int64_t{0}, std::int64_t{1}, std::int64_t{42}, std::int64_t{-7}, std::int64_t{1} << 40,
+                           std::int64_t{123456789012345}}) {
+    for (std::uint32_t ranks : {2u, 8u}) {
+      std::printf("%s\"%lld/%u\": %u", first ? "" : ", ", static_cast<long long>(key), ranks,
+                  cuco::b200::exchange_owner(static_cast<std::uint64_t>(key), 0x9E3779B97F4A7C15ull, ranks));
+      first = false;
+    }
+  }
+  std::printf("}, ");
+}
+
 int main()
 {
   hash_vectors();
+  exchange_host_logic();
   fast_int_identities<std::int32_t>();
   fast_int_identities<std::uint32_t>();
   fast_int_identities<std::int64_t>();
@@ -296,6 +375,7 @@ int main()
   pair_layout();
   std::printf("{");
   print_primes();
+  print_owners();
   std::printf("\"total\": %d, \"failed\": %d, \"failures\": [", g_total, g_failed);
   for (std::size_t i = 0; i < g_failures.size(); ++i) {
     std::printf("%s\"%s\"", i ? ", " : "", g_failures[i].c_str());

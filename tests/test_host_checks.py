@@ -43,3 +43,14 @@ def test_prime_table_regenerates_identically(tmp_path):
     subprocess.run(["python", str(ROOT / "tools" / "gen_prime_table.py"), "-o", str(out)], check=True,
                    capture_output=True)
     assert out.read_text() == (ROOT / "include" / "cuco" / "b200" / "prime_table.hpp").read_text()
+
+
+def test_owner_function_matches_its_python_restatement(report):
+    """exchange_owner (include/cuco/b200/bulk_kernels.cuh) is restated in Python by the gloo test's stand-in
+    router (tests/test_partitioned_gloo.py::owner_of): both must agree, or the CPU multi-process tests would
+    exercise a different partition than the GPU path."""
+    from test_partitioned_gloo import owner_of
+    assert len(report["owners"]) == 12
+    for name, owner in report["owners"].items():
+        key, ranks = name.split("/")
+        assert owner == owner_of(int(key), 0x9E3779B97F4A7C15, int(ranks)), name
