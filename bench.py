@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the hot path on BASELINE.json's headline configuration.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--detail]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--no-points] [--no-c4] [--no-c5]
 
 Workload (config[1] of BASELINE.json, the one the metric is quoted on): cuco::static_map<int64,int64>,
 100 M uniform key/value pairs (uniform_int[1, n] -> ~63 % distinct, value = key, fixed seed) bulk
@@ -13,10 +13,15 @@ reference's own static_set/insert_or_apply benchmarks do the same, SURVEY.md §6
 (1.6 GB of pairs, 3.2 GB of slots) are far larger than the 126 MB L2, so nothing carries over
 between timed kernels.
 
-N > 1 (torchrun, one rank per GPU): the hash-partitioned table of BASELINE config[3]; every rank
-brings its own 100 M pairs (weak scaling), keys are routed to their owner rank with an NCCL
-all-to-all, inserted locally, and lookups return the same way.  Timing is CUDA events per rank, max
-over ranks.
+N > 1 (torchrun, one rank per GPU): the hash-partitioned table (cucollections_b200/partitioned.py). First a
+checker leg, never timed: 1 M pairs per rank through the routing under test, every rank's mixed hit / miss
+find / contains and the global size() compared bit-exactly with the CPU oracle over the union of all batches
+(non-zero exit on mismatch). Then the headline: every rank brings its own 100 M pairs (weak scaling), keys are
+grouped by owner rank locally, delivered over NVLink by the copy engines while the owners apply what has
+already landed, and lookups return the same way (staged exchange; `CUCO_B200_ROUTING=fused|nccl` select the
+round-1 paths). Timing is CUDA events per rank, max over ranks. Extra legs in the same line: `c4` = BASELINE
+configs[3] at its stated size (4 B pairs over the N GPUs), `c5` = configs[4] (insert_or_apply sum over 2 B
+rows with 10 M distinct keys, with and without per-GPU pre-aggregation).
 
 `--impl reference` times cuco's own headers (oracle/_ref/libcuco_ref.so: the unmodified reference
 compiled for sm_100a behind the same C shim) on the same inputs with the same events - that is the
