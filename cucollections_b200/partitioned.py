@@ -764,8 +764,13 @@ class partitioned_static_map:
 
     def __init__(self, n_total, load_factor=0.5, *, backend, group=None, salt=DEFAULT_SALT,
                  headroom=1.03, fused_batch=None, fused_lanes=None, routing=None, **table_kw):
-        """`fused_batch`: largest batch (elements per rank and call) the fused exchange path is sized
-        for; None keeps the all_to_all routing (also the fallback for spilled elements).
+        """`fused_batch`: largest batch (elements per rank and call) the exchange buffers are sized for;
+        None keeps the all_to_all routing (also the fallback for spilled elements). It is a contract of
+        the collective: every rank may pass batches of any size up to it (ragged and empty batches are
+        fine - all ranks always run the same number of exchange rounds), but a rank that exceeds it
+        raises ValueError before it takes part in the call and leaves its peers waiting, like a size
+        mismatch in any collective. `routing`: "staged" (default; copy-engine transfers overlapped with the
+        owners' probes), "fused" (round 1: peer stores from the routing kernel) or "nccl".
         `fused_lanes`: chunks per batch that are software-pipelined (routing of chunk c+1 overlaps the
         owner-side probe of chunk c); default 1 or CUCO_B200_EXCHANGE_LANES."""
         self.group = group
